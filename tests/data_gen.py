@@ -1,0 +1,96 @@
+"""Synthetic reference / read generator.
+
+Test and benchmark infrastructure: a small C generator (tests/csrc/simgen.c)
+driven through ctypes.  Not part of the product path.
+"""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "csrc", "libsimgen.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "csrc", "simgen.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", _SO, src, "-lm"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.sim_reference.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+        _lib.sim_plant_repeats.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_double]
+        _lib.sim_reads.restype = ctypes.c_uint64
+        _lib.sim_reads.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                   ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    return _lib
+
+
+def make_reference(seed, contig_lens, n_repeats=0, rep_min=300, rep_max=6000, rep_div=0.05):
+    """Returns (ref uint8 array of ASCII bases, contig offsets uint64[n+1], names)."""
+    contig_lens = [int(x) for x in contig_lens]
+    coff = np.zeros(len(contig_lens) + 1, dtype=np.uint64)
+    coff[1:] = np.cumsum(contig_lens)
+    total = int(coff[-1])
+    ref = np.empty(total, dtype=np.uint8)
+    lib().sim_reference(seed, total, ref.ctypes.data)
+    if n_repeats:
+        lib().sim_plant_repeats(seed + 1000, ref.ctypes.data, total, n_repeats, rep_min, rep_max, rep_div)
+    names = ["chr%d" % (i + 1) for i in range(len(contig_lens))]
+    return ref, coff, names
+
+
+def make_reads(seed, ref, coff, n_reads, len_min=1000, len_max=10000, len_mean=0.0, len_sd=0.0,
+               p_sub=0.03, p_ins=0.02, p_del=0.03):
+    """Returns (buf uint8, offsets uint64[n+1], truth int64[n,4] = ctg,start,end,strand)."""
+    cap = int(n_reads * (len_max * 1.25 + 64))
+    buf = np.empty(cap, dtype=np.uint8)
+    offs = np.empty(n_reads + 1, dtype=np.uint64)
+    truth = np.empty((n_reads, 4), dtype=np.int64)
+    n = lib().sim_reads(seed, ref.ctypes.data, len(coff) - 1, coff.ctypes.data, n_reads, len_min, len_max,
+                        len_mean, len_sd, p_sub, p_ins, p_del, buf.ctypes.data, offs.ctypes.data, truth.ctypes.data)
+    return buf[:n].copy(), offs, truth
+
+
+def write_fasta(path, ref, coff, names, width=80):
+    with open(path, "wb") as fh:
+        for i, nm in enumerate(names):
+            fh.write(b">" + nm.encode() + b"\n")
+            s = ref[int(coff[i]):int(coff[i + 1])]
+            for j in range(0, len(s), width):
+                fh.write(s[j:j + width].tobytes() + b"\n")
+
+
+def reads_as_list(buf, offs):
+    b = buf.tobytes()
+    return [b[int(offs[i]):int(offs[i + 1])].decode() for i in range(len(offs) - 1)]
+
+
+# BASELINE.md section 3 configurations ------------------------------------------------
+GRCH38_LENS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+               138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+               83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+
+
+def config1_reference():
+    return make_reference(1, [5_000_000])
+
+
+def config1_reads(ref, coff, n_reads=200_000):
+    return make_reads(2, ref, coff, n_reads, 1000, 10000, p_sub=0.03, p_ins=0.02, p_del=0.03)
+
+
+def config2_contig_lens(total=3_100_000_000):
+    s = float(sum(GRCH38_LENS))
+    return [int(round(x / s * total)) for x in GRCH38_LENS]
