@@ -1,0 +1,307 @@
+/* chain.cu -- anchor chaining: warp-cooperative DP, backtrack, chain compaction
+ * (north-star (d)), one warp per read.
+ *
+ * Replaces lchain.c mm_lchain_dp (comput_sc, mg_log2), mg_chain_backtrack,
+ * mg_chain_bk_end and compact_a of minimap2 v2.26 on the mm_map path
+ * (/root/reference/src/lib.rs:482,587).  Bit-exact, including the max_skip
+ * early exit, the t[] marks, the `max_ii` shortcut and upstream's unstable sort
+ * of chain ends.
+ *
+ * DP.  Anchor i scans its predecessors j = i-1 .. st in steps of 32 lanes
+ * (descending j = ascending lane).  Upstream's loop carries three serial pieces
+ * of state; each has a warp form that gives the same result:
+ *   - max_f/max_j (strict improvement, first best wins): exclusive prefix max
+ *     over the lanes tells every lane whether it WOULD have improved;
+ *   - t[] marks (t[p[j]] = i): marks only ever point to smaller j, i.e. to
+ *     later lanes or later steps, so "all lanes store, __syncwarp, all lanes
+ *     load" shows every lane exactly the marks of its predecessors; marks
+ *     stored by lanes past the break point are never read again for this i;
+ *   - n_skip (saturating counter, break above max_skip): replayed over the
+ *     ballot bits of improving / marked lanes (closed form when nothing is marked).
+ * f/p/t live in HBM slices of the read (L1/L2 resident while the read is active).
+ * Bound: INT32 issue + L1 latency of the i -> i+1 dependency - see DESIGN.md.
+ */
+#include "dev_common.cuh"
+#include "dev_sort.cuh"
+#include "stages.h"
+
+#define INT32_MIN_ (-2147483647 - 1)
+
+__device__ __forceinline__ float dev_mg_log2(float x) /* lchain.c mg_log2; x >= 2 */
+{
+	uint32_t zi = __float_as_uint(x);
+	float log_2 = (float)(((zi >> 23) & 255u) - 128u);
+	zi &= ~(255u << 23);
+	zi += 127u << 23;
+	float zf = __uint_as_float(zi);
+	float t = __fadd_rn(__fmul_rn(-0.34484843f, zf), 2.02466578f);
+	t = __fsub_rn(__fmul_rn(t, zf), 0.67487759f);
+	return __fadd_rn(log_2, t);
+}
+
+__device__ __forceinline__ int32_t dev_comput_sc(uint64_t aix, uint64_t aiy, uint64_t ajx, uint64_t ajy,
+                                                 int32_t max_dist_x, int32_t max_dist_y, int32_t bw, float pen_gap, float pen_skip)
+{
+	int32_t dq = (int32_t)aiy - (int32_t)ajy, dr, dd, dg, q_span, sc;
+	if (dq <= 0 || dq > max_dist_x) return INT32_MIN_;
+	dr = (int32_t)(aix - ajx);
+	if (dr == 0 || dq > max_dist_y) return INT32_MIN_;
+	dd = dr > dq ? dr - dq : dq - dr;
+	if (dd > bw) return INT32_MIN_;
+	dg = dr < dq ? dr : dq;
+	q_span = (int32_t)(ajy >> 32 & 0xff);
+	sc = q_span < dg ? q_span : dg;
+	if (dd || dg > q_span) {
+		float lin_pen = __fadd_rn(__fmul_rn(pen_gap, (float)dd), __fmul_rn(pen_skip, (float)dg));
+		float log_pen = dd >= 1 ? dev_mg_log2((float)(dd + 1)) : 0.0f;
+		sc -= (int)__fadd_rn(lin_pen, __fmul_rn(.5f, log_pen));
+	}
+	return sc;
+}
+
+__global__ void __launch_bounds__(CHAIN_WARPS * 32)
+chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
+{
+	const int lane = mmg_lane();
+	unsigned long long tot_iter = 0, tot_anchor = 0;
+	for (;;) {
+		uint32_t r = r0 + mmg_next_item(work);
+		if (r >= r1) break;
+		const int n = (int)c.n_a[r];
+		const uint64_t ab = c.a_off[r] - c.a_off0;
+		const int qlen = (int)(c.off[r + 1] - c.off[r]);
+		const uint64_t *ax = c.bx + ab, *ay = c.by + ab;
+		int32_t *f = c.f + ab, *p = c.p + ab, *t = c.t + ab;
+		/* map.c mm_map_frag: chaining gaps */
+		int32_t max_dist_y = o.max_gap, max_dist_x;
+		if (o.max_gap_ref > 0) max_dist_x = o.max_gap_ref;
+		else if (o.max_frag_len > 0) { max_dist_x = o.max_frag_len - qlen; if (max_dist_x < o.max_gap) max_dist_x = o.max_gap; }
+		else max_dist_x = o.max_gap;
+		if (max_dist_x < o.bw) max_dist_x = o.bw;
+		if (max_dist_y < o.bw) max_dist_y = o.bw;
+		const int32_t bw = o.bw, max_skip = o.max_chain_skip, max_iter = o.max_chain_iter;
+		const float pen_gap = o.chn_pen_gap, pen_skip = o.chn_pen_skip;
+
+		int st = 0, max_ii = -1;
+		uint64_t mii_x = 0;
+		int32_t mii_f = 0;
+		for (int i = 0; i < n; ++i) {
+			const uint64_t aix = ax[i], aiy = ay[i];
+			/* advance st: first j that shares the target strand and is within max_dist_x */
+			for (;;) {
+				int j = st + lane;
+				bool out = j < i && ((ax[j] >> 32) != (aix >> 32) || aix > ax[j] + (uint64_t)max_dist_x);
+				uint32_t m = __ballot_sync(MMG_FULL, out);
+				int lead = m == MMG_FULL ? 32 : __ffs((int)~m) - 1;
+				st += lead;
+				if (lead < 32) break;
+			}
+			if (i - st > max_iter) st = i - max_iter;
+			int32_t max_f = (int32_t)(aiy >> 32 & 0xff), n_skip = 0;
+			int max_j = -1, end_j = st - 1;
+			bool broke = false;
+			for (int jb = i - 1; jb >= st && !broke; jb -= 32) {
+				const int j = jb - lane;
+				const bool inr = j >= st;
+				int32_t sc = INT32_MIN_, pj = -1;
+				if (inr) {
+					sc = dev_comput_sc(aix, aiy, ax[j], ay[j], max_dist_x, max_dist_y, bw, pen_gap, pen_skip);
+					if (sc != INT32_MIN_) { sc += f[j]; pj = p[j]; }
+				}
+				const bool ok = sc != INT32_MIN_;
+				if (ok && pj >= 0) t[pj] = i;
+				__syncwarp();
+				const bool marked = ok && t[j] == i;
+				/* would lane improve max_f?  exclusive prefix max over earlier lanes and the carried max_f */
+				int32_t incl = sc;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					int32_t v = __shfl_up_sync(MMG_FULL, incl, d);
+					if (lane >= d && v > incl) incl = v;
+				}
+				int32_t excl = __shfl_up_sync(MMG_FULL, incl, 1);
+				if (lane == 0 || excl < max_f) excl = max_f;
+				const bool improve = ok && sc > excl;
+				const uint32_t I = __ballot_sync(MMG_FULL, improve), M = __ballot_sync(MMG_FULL, marked && !improve);
+				int brk = -1;
+				if (M == 0) { n_skip -= __popc(I); if (n_skip < 0) n_skip = 0; }
+				else {
+					uint32_t bits = I | M;
+					while (bits) {
+						int b = __ffs((int)bits) - 1;
+						bits &= bits - 1;
+						if (I >> b & 1u) { if (n_skip > 0) --n_skip; }
+						else if (++n_skip > max_skip) { brk = b; break; }
+					}
+				}
+				const int limit = brk >= 0 ? brk : 32;
+				const int32_t c2 = lane < limit ? sc : INT32_MIN_;
+				const int32_t mx = __reduce_max_sync(MMG_FULL, c2);
+				if (mx > max_f) {
+					max_f = mx;
+					max_j = jb - (__ffs((int)__ballot_sync(MMG_FULL, c2 == mx)) - 1);
+				}
+				if (brk >= 0) end_j = jb - brk, broke = true;
+			}
+			tot_iter += broke ? i - end_j : i - st;
+			/* lchain.c: the best-scoring anchor in range is tried even if the loop stopped before it */
+			if (max_ii < 0 || aix - mii_x > (uint64_t)(int64_t)max_dist_x) {
+				int32_t best = INT32_MIN_;
+				int bestj = -1;
+				for (int jb = i - 1; jb >= st; jb -= 32) {
+					int j = jb - lane;
+					if (j >= st) { int32_t v = f[j]; if (v > best) best = v, bestj = j; }
+				}
+				int32_t mx = __reduce_max_sync(MMG_FULL, best);
+				int cj = best == mx ? bestj : -1;
+				max_ii = __reduce_max_sync(MMG_FULL, cj);
+				if (max_ii >= 0) mii_x = ax[max_ii], mii_f = f[max_ii];
+			}
+			if (max_ii >= 0 && max_ii < end_j) {
+				int32_t tmp = dev_comput_sc(aix, aiy, mii_x, ay[max_ii], max_dist_x, max_dist_y, bw, pen_gap, pen_skip);
+				if (tmp != INT32_MIN_ && max_f < tmp + mii_f) max_f = tmp + mii_f, max_j = max_ii;
+			}
+			if (lane == 0) f[i] = max_f, p[i] = max_j, t[i] = 0;
+			if (max_ii < 0 || (aix - mii_x <= (uint64_t)(int64_t)max_dist_x && mii_f < max_f))
+				max_ii = i, mii_x = aix, mii_f = max_f;
+			__syncwarp();
+		}
+		tot_anchor += n;
+	}
+	if (lane == 0 && tot_anchor) {
+		atomicAdd(&c.stats[4], tot_anchor);
+		atomicAdd(&c.stats[5], tot_iter);
+	}
+}
+
+/* lchain.c: mg_chain_bk_end */
+__device__ __forceinline__ int dev_chain_bk_end(int32_t max_drop, int32_t zkx, int zky, const int32_t *f, const int32_t *p, int32_t *t)
+{
+	int i = zky, end_i = -1, max_i = i;
+	int32_t max_s = 0;
+	if (i < 0 || t[i] != 0) return i;
+	do {
+		int32_t s;
+		t[i] = 2;
+		end_i = i = p[i];
+		s = i < 0 ? zkx : zkx - f[i];
+		if (s > max_s) max_s = s, max_i = i;
+		else if (max_s - s > max_drop) break;
+	} while (i >= 0 && t[i] == 0);
+	for (i = zky; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
+	return max_i;
+}
+
+/* Shared by the DP path and the RMQ re-chain: mg_chain_backtrack + compact_a.
+ * In: sorted anchors ax/ay[n], f/p/t/v[n] (t is cleared here), scratch zx/zy[2n], cx/cy[n].
+ * Out: chained anchors back in ax/ay[0..n_v), u[0..n_u). */
+__device__ void dev_backtrack_compact(int n, uint64_t *ax, uint64_t *ay, const int32_t *f, const int32_t *p, int32_t *t, int32_t *v,
+                                      uint64_t *zx, uint64_t *zy, uint64_t *cx, uint64_t *cy, uint64_t *u,
+                                      int32_t min_cnt, int32_t min_sc, int32_t max_drop, int *bkt, int *n_u_, int *n_v_)
+{
+	const int lane = mmg_lane();
+	const uint32_t lt = mmg_lanemask_lt();
+	int n_z = 0, n_u = 0, n_v = 0;
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		int i = i0 + lane;
+		int32_t fv = i < n ? f[i] : INT32_MIN_;
+		bool keep = i < n && fv >= min_sc;
+		uint32_t km = __ballot_sync(MMG_FULL, keep);
+		if (keep) { int d = n_z + __popc(km & lt); zx[d] = (uint64_t)(int64_t)fv, zy[d] = (uint64_t)i; }
+		n_z += __popc(km);
+		if (i < n) t[i] = 0;
+	}
+	__syncwarp();
+	if (n_z > 0) {
+		if (lane == 0) {
+			dev_radix_sort_128x(zx, zy, n_z, bkt, (int*)v);
+			for (int k = n_z - 1; k >= 0; --k) {
+				int zi = (int)zy[k];
+				if (t[zi] == 0) {
+					int n_v0 = n_v, i;
+					int32_t zkx = (int32_t)zx[k], sc;
+					int end_i = dev_chain_bk_end(max_drop, zkx, zi, f, p, t);
+					/* v[] doubles as the sort's range stack above; it is free again here */
+					for (i = zi; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
+					sc = i < 0 ? zkx : zkx - f[i];
+					if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint32_t)(n_v - n_v0);
+					else n_v = n_v0;
+				}
+			}
+		}
+		n_u = __shfl_sync(MMG_FULL, n_u, 0);
+		n_v = __shfl_sync(MMG_FULL, n_v, 0);
+	}
+	__syncwarp();
+	if (n_u > 0) {
+		/* compact_a: chains in forward order into cx/cy */
+		int k0 = 0;
+		for (int ci = 0; ci < n_u; ++ci) {
+			int ni = (int)(uint32_t)u[ci];
+			for (int j = lane; j < ni; j += 32) {
+				int src = v[k0 + (ni - j - 1)];
+				cx[k0 + j] = ax[src], cy[k0 + j] = ay[src];
+			}
+			k0 += ni;
+		}
+		__syncwarp();
+		/* order chains by the target position of their first anchor (radix_sort_128x on w[]) */
+		if (lane == 0) {
+			int k = 0;
+			for (int ci = 0; ci < n_u; ++ci) {
+				zx[ci] = cx[k], zy[ci] = (uint64_t)k << 32 | (uint32_t)ci;
+				k += (int)(uint32_t)u[ci];
+			}
+			dev_radix_sort_128x(zx, zy, n_u, bkt, (int*)t);
+			for (int ci = 0; ci < n_u; ++ci) zx[n_u + ci] = u[(uint32_t)zy[ci]];
+			for (int ci = 0; ci < n_u; ++ci) u[ci] = zx[n_u + ci];
+		}
+		__syncwarp();
+		k0 = 0;
+		for (int ci = 0; ci < n_u; ++ci) {
+			int ni = (int)(uint32_t)u[ci], src0 = (int)(zy[ci] >> 32);
+			for (int j = lane; j < ni; j += 32) ax[k0 + j] = cx[src0 + j], ay[k0 + j] = cy[src0 + j];
+			k0 += ni;
+		}
+		__syncwarp();
+	}
+	*n_u_ = n_u, *n_v_ = n_v;
+}
+
+__global__ void __launch_bounds__(CHAIN_WARPS * 32)
+backtrack_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
+{
+	__shared__ int s_bkt[CHAIN_WARPS][512];
+	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
+	for (;;) {
+		uint32_t r = r0 + mmg_next_item(work);
+		if (r >= r1) break;
+		const int n = (int)c.n_a[r];
+		const uint64_t ab = c.a_off[r] - c.a_off0;
+		int n_u = 0, n_v = 0;
+		if (n > 0)
+			dev_backtrack_compact(n, c.bx + ab, c.by + ab, c.f + ab, c.p + ab, c.t + ab, c.v + ab,
+			                      c.zx + 2 * ab, c.zy + 2 * ab, c.cx + ab, c.cy + ab, c.u + ab,
+			                      o.min_cnt, o.min_chain_score, o.bw, s_bkt[wib], &n_u, &n_v);
+		if (lane == 0) c.n_u[r] = (uint32_t)n_u, c.n_v[r] = (uint32_t)n_v;
+		__syncwarp();
+	}
+}
+
+int launch_chain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work)
+{
+	int grid = n_sms * 12, need = ((int)(r1 - r0) + CHAIN_WARPS - 1) / CHAIN_WARPS;
+	if (grid > need) grid = need;
+	if (grid < 1) grid = 1;
+	MMG_LAUNCH(chain_dp_kernel, grid, CHAIN_WARPS * 32, 0, st, c, o, r0, r1, work);
+	return 0;
+}
+
+int launch_backtrack(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work)
+{
+	int grid = n_sms * 12, need = ((int)(r1 - r0) + CHAIN_WARPS - 1) / CHAIN_WARPS;
+	if (grid > need) grid = need;
+	if (grid < 1) grid = 1;
+	MMG_LAUNCH(backtrack_kernel, grid, CHAIN_WARPS * 32, 0, st, c, o, r0, r1, work);
+	return 0;
+}

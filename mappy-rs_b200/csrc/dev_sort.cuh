@@ -1,0 +1,79 @@
+/* dev_sort.cuh -- exact device replay of minimap2's radix_sort_128x.
+ *
+ * ksort.h KRADIX_SORT_INIT (v2.26) is an in-place MSD "American flag" sort with
+ * insertion sort below 65 elements.  It is not stable, and the order in which
+ * it leaves equal keys decides chaining tie-breaks (chain ends with equal f in
+ * mg_chain_backtrack, equal anchor positions, equal region keys), so wherever
+ * equal keys can occur the device must reproduce that permutation, not just a
+ * sorted order.  The permutation step is a pointer chase with no parallel form;
+ * it is replayed by ONE lane per read while the rest of the chunk's reads run
+ * on other warps.  Passes over key bytes that are identical in every element
+ * move nothing and are skipped (the result is identical by construction).
+ * Records are (x, y) pairs in separate arrays; the key is x.
+ */
+#ifndef MMG_DEV_SORT_CUH
+#define MMG_DEV_SORT_CUH
+#include "dev_common.cuh"
+
+__device__ __forceinline__ void dev_insertsort_128x(uint64_t *x, uint64_t *y, int beg, int end)
+{
+	for (int i = beg + 1; i < end; ++i)
+		if (x[i] < x[i - 1]) {
+			uint64_t tx = x[i], ty = y[i];
+			int j;
+			for (j = i; j > beg && tx < x[j - 1]; --j) x[j] = x[j - 1], y[j] = y[j - 1];
+			x[j] = tx, y[j] = ty;
+		}
+}
+
+/* bkt: 512 ints of scratch (bucket begin/end); stk: 3 ints per pending range, at least 3*(n/65+1) ints */
+static __device__ void dev_radix_sort_128x(uint64_t *x, uint64_t *y, int n, int *bkt, int *stk)
+{
+	if (n <= 64) { dev_insertsort_128x(x, y, 0, n); return; }
+	int *bb = bkt, *be = bkt + 256;
+	uint64_t diff = 0;
+	for (int i = 1; i < n; ++i) diff |= x[i] ^ x[0];
+	if (diff == 0) return;
+	int s0 = ((63 - __clzll((long long)diff)) >> 3) << 3; /* highest key byte that differs */
+	int sp = 0;
+	stk[0] = 0, stk[1] = n, stk[2] = s0, sp = 1;
+	while (sp > 0) {
+		--sp;
+		const int beg = stk[3 * sp], end = stk[3 * sp + 1], s = stk[3 * sp + 2];
+		for (int k = 0; k < 256; ++k) be[k] = 0;
+		for (int i = beg; i < end; ++i) ++be[(x[i] >> s) & 255];
+		{
+			int pos = beg;
+			for (int k = 0; k < 256; ++k) { int cnt = be[k]; bb[k] = pos; pos += cnt; be[k] = pos; }
+		}
+		for (int k = 0; k < 256;) {
+			if (bb[k] != be[k]) {
+				int l = (int)((x[bb[k]] >> s) & 255);
+				if (l != k) {
+					uint64_t tx = x[bb[k]], ty = y[bb[k]];
+					do {
+						uint64_t sx = tx, sy = ty;
+						int q = bb[l]++;
+						tx = x[q], ty = y[q];
+						x[q] = sx, y[q] = sy;
+						l = (int)((tx >> s) & 255);
+					} while (l != k);
+					x[bb[k]] = tx, y[bb[k]] = ty;
+					++bb[k];
+				} else ++bb[k];
+			} else ++k;
+		}
+		if (s) {
+			const int s2 = s > 8 ? s - 8 : 0;
+			int start = beg;
+			for (int k = 0; k < 256; ++k) {
+				int e = be[k], sz = e - start;
+				if (sz > 64) stk[3 * sp] = start, stk[3 * sp + 1] = e, stk[3 * sp + 2] = s2, ++sp;
+				else if (sz > 1) dev_insertsort_128x(x, y, start, e);
+				start = e;
+			}
+		}
+	}
+}
+
+#endif

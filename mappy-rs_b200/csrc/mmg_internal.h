@@ -1,0 +1,47 @@
+/* mmg_internal.h -- shared declarations of the B200 mapping library (libmmg.so).
+ * Host index (flat layout, ready for upload), device views, pipeline types. */
+#ifndef MMG_INTERNAL_H
+#define MMG_INTERNAL_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include "../../include/mmg.h"
+
+#define MMG_EMPTY_KEY 0xffffffffffffffffULL
+
+/* Host-side index in the layout that is uploaded verbatim.
+ *
+ * Upstream keeps 2^b khash tables (index.c: mm_idx_bucket_t); a GPU lookup wants
+ * one probe = one 16-byte load, so the buckets are flattened into a single
+ * open-addressing table (linear probing, load factor <= 0.5):
+ *   slot.key = minimizer<<1 | is_single   (MMG_EMPTY_KEY when free)
+ *   slot.val = position word y            (is_single)
+ *            = offset<<32 | count into pos[]  (otherwise; runs sorted ascending)
+ * which is the same key/value encoding index.c: worker_post() stores. */
+struct mmg_index {
+	int32_t k, w, b, flag;
+	uint32_t n_seq;
+	std::vector<std::string> names;
+	std::vector<uint32_t> lens;
+	std::vector<uint64_t> offs;        /* n_seq + 1 */
+	std::vector<uint32_t> S;           /* 4 bits per base (index.c: mm_seq4_set) */
+	uint32_t hbits;                    /* table has 1<<hbits slots */
+	std::vector<uint64_t> hkeys, hvals;
+	std::vector<uint64_t> pos;
+	uint64_t n_keys;
+};
+
+static inline uint64_t mmg_hash_slot(uint64_t minier, uint32_t hbits)
+{
+	return (minier * 0x9E3779B97F4A7C15ULL) >> (64 - hbits);
+}
+
+/* index_host.cpp */
+int mmg_host_sketch(const char *seq, int len, int w, int k, uint32_t rid, std::vector<uint64_t> &xs, std::vector<uint64_t> &ys);
+const uint64_t *mmg_index_lookup(const mmg_index *idx, uint64_t minier, int *n);
+int32_t mmg_index_cal_max_occ(const mmg_index *idx, float f);
+void mmg_set_error(const char *fmt, ...);
+
+#endif

@@ -1,0 +1,416 @@
+/* pipeline.cu -- the device pipeline behind mmg_map_batch().
+ *
+ * Replaces, for the mappy-rs host, the per-read `mm_map` calls of `Aligner.map`
+ * and of the `map_batch` worker threads (/root/reference/src/lib.rs:482-488,
+ * 541-636): a batch of reads is cut into chunks sized for the device arenas,
+ * and every chunk runs sketch -> seed -> expand -> sort -> chain -> backtrack
+ * -> (re-chain) -> regions/mapq as one kernel per stage with one warp (or CTA)
+ * per read.  The index is uploaded once at mmg_aligner_create() and stays
+ * resident (north-star (a)).  There is no CPU mapping path.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "mmg_internal.h"
+#include "dev_common.cuh"
+#include "stages.h"
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { mmg_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return MMG_ECUDA; } } while (0)
+
+static const char *g_stage_names[MMG_N_STAGES] = { "h2d", "sketch", "seed", "scan", "expand", "sort", "chain_dp", "backtrack", "rechain", "regs", "extend", "d2h" };
+
+struct mmg_aligner {
+	const mmg_index *idx;
+	mmg_mapopt_t mo;
+	int device, n_sms;
+	cudaStream_t stream;
+	DevIndex di;
+	DevOpt dopt;
+	std::vector<void*> dev_allocs;     /* index + arenas */
+	/* arena capacities */
+	uint64_t cap_bases, cap_anchors, cap_regs;
+	uint32_t cap_reads;
+	bool arenas_ready;
+	ChunkDev cd;                       /* arena pointers */
+	int profile;
+	double stage_ms[MMG_N_STAGES];
+	uint64_t stage_launches[MMG_N_STAGES];
+	cudaEvent_t ev0, ev1;
+};
+
+struct mmg_batch {
+	uint32_t n_reads;
+	uint64_t n_bases;
+	const char *h_bases;               /* caller's buffers (valid until upload returns) */
+	const uint64_t *h_off;
+	char *d_bases; uint64_t *d_off;    /* device-resident inputs */
+	mmg_hit_t *d_hits; uint64_t hits_cap, n_hits_dev;
+	uint32_t *d_nregs;                 /* per read */
+	unsigned long long *d_stats;
+	std::vector<uint64_t> off;         /* host copy of offsets */
+	std::vector<uint64_t> hit_off;
+	std::vector<mmg_hit_t> hits;
+	std::vector<uint32_t> cigar;
+	uint64_t stats[MMG_N_STATS];
+	bool uploaded, ran, fetched;
+	/* debug: arenas of the LAST chunk stay valid until the next run */
+	uint32_t dbg_r0, dbg_r1;
+};
+
+template<typename T> static int dev_alloc(mmg_aligner *al, T **p, uint64_t n)
+{
+	void *q = 0;
+	if (n == 0) n = 1;
+	cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+	if (e != cudaSuccess) { mmg_set_error("cudaMalloc of %llu bytes failed: %s", (unsigned long long)(n * sizeof(T)), cudaGetErrorString(e)); return MMG_ENOMEM; }
+	al->dev_allocs.push_back(q);
+	*p = (T*)q;
+	return MMG_OK;
+}
+
+static int upload_index(mmg_aligner *al)
+{
+	const mmg_index *idx = al->idx;
+	DevIndex &di = al->di;
+	di.k = idx->k, di.w = idx->w, di.b = idx->b, di.flag = idx->flag, di.n_seq = idx->n_seq, di.hbits = idx->hbits;
+	size_t nslots = idx->hkeys.size();
+	std::vector<mmg_u128> tab(nslots);
+	for (size_t i = 0; i < nslots; ++i) tab[i].x = idx->hkeys[i], tab[i].y = idx->hvals[i];
+	mmg_u128 *d_tab; uint64_t *d_pos, *d_soff; uint32_t *d_S, *d_slen;
+	int rc;
+	if ((rc = dev_alloc(al, &d_tab, nslots))) return rc;
+	if ((rc = dev_alloc(al, &d_pos, idx->pos.size()))) return rc;
+	if ((rc = dev_alloc(al, &d_S, idx->S.size()))) return rc;
+	if ((rc = dev_alloc(al, &d_soff, idx->offs.size()))) return rc;
+	if ((rc = dev_alloc(al, &d_slen, idx->lens.size()))) return rc;
+	CK(cudaMemcpy(d_tab, tab.data(), nslots * sizeof(mmg_u128), cudaMemcpyHostToDevice));
+	if (!idx->pos.empty()) CK(cudaMemcpy(d_pos, idx->pos.data(), idx->pos.size() * 8, cudaMemcpyHostToDevice));
+	if (!idx->S.empty()) CK(cudaMemcpy(d_S, idx->S.data(), idx->S.size() * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d_soff, idx->offs.data(), idx->offs.size() * 8, cudaMemcpyHostToDevice));
+	if (!idx->lens.empty()) CK(cudaMemcpy(d_slen, idx->lens.data(), idx->lens.size() * 4, cudaMemcpyHostToDevice));
+	di.htab = d_tab, di.pos = d_pos, di.S = d_S, di.seq_off = d_soff, di.seq_len = d_slen;
+	return MMG_OK;
+}
+
+static void fill_devopt(mmg_aligner *al)
+{
+	const mmg_mapopt_t &m = al->mo;
+	DevOpt &o = al->dopt;
+	memset(&o, 0, sizeof(o));
+	o.flag = m.flag, o.seed = m.seed;
+	o.bw = m.bw, o.bw_long = m.bw_long, o.max_gap = m.max_gap, o.max_gap_ref = m.max_gap_ref, o.max_frag_len = m.max_frag_len;
+	o.max_chain_skip = m.max_chain_skip, o.max_chain_iter = m.max_chain_iter, o.min_cnt = m.min_cnt, o.min_chain_score = m.min_chain_score;
+	/* map.c mm_map_frag: float = float * double * int, evaluated in double */
+	o.chn_pen_gap = (float)(m.chain_gap_scale * 0.01 * al->idx->k);
+	o.chn_pen_skip = (float)(m.chain_skip_scale * 0.01 * al->idx->k);
+	o.rmq_size_cap = m.rmq_size_cap, o.rmq_inner_dist = m.rmq_inner_dist, o.rmq_rescue_size = m.rmq_rescue_size, o.rmq_rescue_ratio = m.rmq_rescue_ratio;
+	o.mask_level = m.mask_level, o.mask_len = m.mask_len, o.pri_ratio = m.pri_ratio, o.best_n = m.best_n, o.alt_drop = m.alt_drop;
+	o.a = m.a, o.b = m.b, o.q = m.q, o.e = m.e, o.q2 = m.q2, o.e2 = m.e2, o.sc_ambi = m.sc_ambi;
+	o.zdrop = m.zdrop, o.zdrop_inv = m.zdrop_inv, o.end_bonus = m.end_bonus, o.min_dp_max = m.min_dp_max, o.min_ksw_len = m.min_ksw_len;
+	o.anchor_ext_len = m.anchor_ext_len, o.anchor_ext_shift = m.anchor_ext_shift, o.max_clip_ratio = m.max_clip_ratio;
+	o.q_occ_frac = m.q_occ_frac, o.mid_occ = m.mid_occ, o.max_max_occ = m.max_max_occ, o.occ_dist = m.occ_dist, o.max_qlen = m.max_qlen;
+	o.max_sw_mat = m.max_sw_mat;
+}
+
+static int alloc_arenas(mmg_aligner *al)
+{
+	if (al->arenas_ready) return MMG_OK;
+	ChunkDev &c = al->cd;
+	const uint64_t B = al->cap_bases, A = al->cap_anchors, R = al->cap_reads, G = al->cap_regs;
+	int rc = 0;
+#define AL(ptr, n) if ((rc = dev_alloc(al, &(ptr), (n)))) return rc
+	AL(c.mz_x, B); AL(c.mz_y, B); AL(c.n_mz, R);
+	AL(c.sd_val, B); AL(c.sd_n, B); AL(c.sd_qpos, B); AL(c.sd_meta, B);
+	AL(c.n_seed, R); AL(c.n_a, R); AL(c.rep_len, R); AL(c.a_off, R + 1);
+	AL(c.ax, A); AL(c.ay, A); AL(c.bx, A); AL(c.by, A);
+	AL(c.f, A); AL(c.p, A); AL(c.t, A); AL(c.v, A);
+	AL(c.zx, 2 * A); AL(c.zy, 2 * A);
+	AL(c.cx, A); AL(c.cy, A); AL(c.u, A);
+	AL(c.n_u, R); AL(c.n_v, R); AL(c.r_off, R + 1);
+	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
+	AL(c.work, 64); AL(c.flags, R);
+#undef AL
+	al->arenas_ready = true;
+	return MMG_OK;
+}
+
+extern "C" {
+
+int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device, mmg_aligner **out)
+{
+	*out = 0;
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) {
+		mmg_set_error("no CUDA device: libmmg has no CPU mapping path");
+		return MMG_ENODEV;
+	}
+	if (device < 0 || device >= n_dev) { mmg_set_error("device %d out of range (%d devices)", device, n_dev); return MMG_EINVAL; }
+	if ((mo->flag & MMG_F_CIGAR) && (idx->flag & MMG_I_NO_SEQ)) { mmg_set_error("index has no sequence but CIGAR was requested"); return MMG_ENOSEQ; }
+	const int64_t unsup = 0x80LL | 0x100LL | 0x200LL | 0x1000LL | 0x2000LL | MMG_F_FOR_ONLY | MMG_F_REV_ONLY | 0x400000LL | 0x20000000LL | MMG_F_RMQ | 0x100000000LL | 0x1LL | 0x2LL;
+	if (mo->flag & unsup) { mmg_set_error("mapping flag 0x%llx selects a code path outside the supported long-read path", (unsigned long long)(mo->flag & unsup)); return MMG_EUNSUP; }
+	if (idx->flag & MMG_I_HPC) { mmg_set_error("homopolymer-compressed indexes are not supported"); return MMG_EUNSUP; }
+	CK(cudaSetDevice(device));
+	mmg_aligner *al = new mmg_aligner();
+	al->idx = idx, al->mo = *mo, al->device = device;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	al->n_sms = prop.multiProcessorCount;
+	CK(cudaStreamCreateWithFlags(&al->stream, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&al->ev0));
+	CK(cudaEventCreate(&al->ev1));
+	al->arenas_ready = false;
+	al->profile = 0;
+	al->cap_bases = (uint64_t)96 << 20, al->cap_reads = 1u << 17, al->cap_anchors = (uint64_t)48 << 20, al->cap_regs = (uint64_t)4 << 20;
+	memset(al->stage_ms, 0, sizeof(al->stage_ms));
+	memset(al->stage_launches, 0, sizeof(al->stage_launches));
+	memset(&al->cd, 0, sizeof(al->cd));
+	int rc = upload_index(al);
+	if (rc) { mmg_aligner_destroy(al); return rc; }
+	fill_devopt(al);
+	*out = al;
+	return MMG_OK;
+}
+
+void mmg_aligner_destroy(mmg_aligner *al)
+{
+	if (!al) return;
+	for (size_t i = 0; i < al->dev_allocs.size(); ++i) cudaFree(al->dev_allocs[i]);
+	if (al->stream) cudaStreamDestroy(al->stream);
+	if (al->ev0) cudaEventDestroy(al->ev0);
+	if (al->ev1) cudaEventDestroy(al->ev1);
+	delete al;
+}
+
+int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
+{
+	if (strcmp(key, "profile") == 0) { al->profile = (int)v; return MMG_OK; }
+	if (al->arenas_ready) { mmg_set_error("arena sizes are fixed after the first batch"); return MMG_EINVAL; }
+	if (strcmp(key, "chunk_bases") == 0) al->cap_bases = (uint64_t)v;
+	else if (strcmp(key, "chunk_reads") == 0) al->cap_reads = (uint32_t)v;
+	else if (strcmp(key, "anchor_cap") == 0) al->cap_anchors = (uint64_t)v;
+	else if (strcmp(key, "regs_cap") == 0) al->cap_regs = (uint64_t)v;
+	else { mmg_set_error("unknown key '%s'", key); return MMG_EINVAL; }
+	return MMG_OK;
+}
+
+int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets, uint32_t n_reads, mmg_batch **out)
+{
+	*out = 0;
+	CK(cudaSetDevice(al->device));
+	mmg_batch *b = new mmg_batch();
+	b->n_reads = n_reads, b->h_bases = bases, b->h_off = offsets;
+	b->n_bases = n_reads ? offsets[n_reads] - offsets[0] : 0;
+	b->off.assign(offsets, offsets + n_reads + 1);
+	b->d_bases = 0, b->d_off = 0, b->d_hits = 0, b->d_nregs = 0, b->d_stats = 0;
+	b->uploaded = b->ran = b->fetched = false;
+	memset(b->stats, 0, sizeof(b->stats));
+	for (uint32_t i = 0; i < n_reads; ++i) {
+		uint64_t l = offsets[i + 1] - offsets[i];
+		if (l > 0x7fffffffULL || l > al->cap_bases) { mmg_set_error("read %u is longer than the chunk capacity (%llu bases)", i, (unsigned long long)al->cap_bases); delete b; return MMG_EINVAL; }
+	}
+	if (cudaMalloc((void**)&b->d_bases, b->n_bases + 64) != cudaSuccess || cudaMalloc((void**)&b->d_off, (size_t)(n_reads + 1) * 8) != cudaSuccess ||
+	    cudaMalloc((void**)&b->d_nregs, (size_t)(n_reads + 1) * 4) != cudaSuccess || cudaMalloc((void**)&b->d_stats, MMG_N_STATS * 8) != cudaSuccess) {
+		mmg_set_error("cudaMalloc failed for the batch inputs");
+		mmg_batch_destroy(b);
+		return MMG_ENOMEM;
+	}
+	b->hits_cap = (uint64_t)n_reads * 6 + 1024;
+	if (cudaMalloc((void**)&b->d_hits, b->hits_cap * sizeof(mmg_hit_t)) != cudaSuccess) { mmg_set_error("cudaMalloc failed for the result pool"); mmg_batch_destroy(b); return MMG_ENOMEM; }
+	if (al->profile) cudaEventRecord(al->ev0, al->stream);
+	/* offsets are rebased so that the device buffer starts at 0 */
+	std::vector<uint64_t> rel(n_reads + 1);
+	for (uint32_t i = 0; i <= n_reads; ++i) rel[i] = offsets[i] - offsets[0];
+	b->off = rel;
+	CK(cudaMemcpyAsync(b->d_bases, bases + offsets[0], b->n_bases, cudaMemcpyHostToDevice, al->stream));
+	CK(cudaMemcpyAsync(b->d_off, rel.data(), (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, al->stream));
+	CK(cudaMemsetAsync(b->d_stats, 0, MMG_N_STATS * 8, al->stream));
+	if (al->profile) cudaEventRecord(al->ev1, al->stream);
+	CK(cudaStreamSynchronize(al->stream));
+	if (al->profile) { float ms = 0; cudaEventElapsedTime(&ms, al->ev0, al->ev1); al->stage_ms[ST_H2D] += ms; }
+	b->uploaded = true;
+	*out = b;
+	return MMG_OK;
+}
+
+#define STAGE_BEGIN() do { if (al->profile) cudaEventRecord(al->ev0, st); } while (0)
+#define STAGE_END(id) do { al->stage_launches[id] += 1; if (al->profile) { float ms_ = 0; cudaEventRecord(al->ev1, st); cudaEventSynchronize(al->ev1); cudaEventElapsedTime(&ms_, al->ev0, al->ev1); al->stage_ms[id] += ms_; } } while (0)
+
+int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
+{
+	if (!b->uploaded) { mmg_set_error("batch not uploaded"); return MMG_EINVAL; }
+	CK(cudaSetDevice(al->device));
+	int rc = alloc_arenas(al);
+	if (rc) return rc;
+	cudaStream_t st = al->stream;
+	memset(al->stage_ms, 0, sizeof(al->stage_ms));
+	memset(al->stage_launches, 0, sizeof(al->stage_launches));
+	b->n_hits_dev = 0;
+	const uint32_t n = b->n_reads;
+	std::vector<uint64_t> h_aoff;
+	for (uint32_t r0 = 0; r0 < n;) {
+		/* chunk = as many reads as fit the base-sized arenas */
+		uint32_t r1 = r0;
+		while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= al->cap_bases) ++r1;
+		if (r1 == r0) { mmg_set_error("read %u does not fit the chunk arenas", r0); return MMG_EINVAL; }
+		ChunkDev c = al->cd;
+		c.n_reads = r1 - r0;
+		c.seq = b->d_bases, c.off = b->d_off + r0, c.off0 = b->off[r0];
+		c.stats = b->d_stats;
+		uint32_t *work = c.work;
+		int wi = 0;
+		CK(cudaMemsetAsync(c.work, 0, 64 * 4, st));
+		CK(cudaMemsetAsync(c.flags, 0, (size_t)c.n_reads * 4, st));
+		STAGE_BEGIN(); launch_sketch(c, al->di, al->n_sms, st, work + wi++); STAGE_END(ST_SKETCH);
+		STAGE_BEGIN(); launch_seed(c, al->di, al->dopt, al->n_sms, st, work + wi++); STAGE_END(ST_SEED);
+		STAGE_BEGIN(); launch_scan_u32(c.n_a, c.a_off, c.n_reads, st); STAGE_END(ST_SCAN);
+		h_aoff.resize(c.n_reads + 1);
+		CK(cudaMemcpyAsync(h_aoff.data(), c.a_off, (size_t)(c.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		/* sub-ranges whose anchors fit the anchor-sized arenas */
+		for (uint32_t s0 = 0; s0 < c.n_reads;) {
+			uint32_t s1 = s0;
+			while (s1 < c.n_reads && h_aoff[s1 + 1] - h_aoff[s0] <= al->cap_anchors) ++s1;
+			if (s1 == s0) { mmg_set_error("read %u has %llu anchors, more than anchor_cap", r0 + s0, (unsigned long long)(h_aoff[s0 + 1] - h_aoff[s0])); return MMG_ENOMEM; }
+			c.a_off0 = h_aoff[s0];
+			if (wi + 8 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
+			STAGE_BEGIN(); launch_expand(c, al->di, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_EXPAND);
+			STAGE_BEGIN(); launch_sort(c, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_SORT);
+			STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
+			STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
+			STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);
+			STAGE_BEGIN();
+			launch_scan_u32(c.n_u + s0, c.r_off + s0, s1 - s0, st);
+			STAGE_END(ST_SCAN);
+			STAGE_BEGIN(); launch_regs(c, al->di, al->dopt, s0, s1, al->cap_regs, al->n_sms, st, work + wi++); STAGE_END(ST_REGS);
+			STAGE_BEGIN();
+			launch_scan_u32(c.n_regs + s0, c.h_off + s0, s1 - s0, st);
+			STAGE_END(ST_SCAN);
+			uint64_t n_hits_sub = 0, n_regs_sub = 0;
+			CK(cudaMemcpyAsync(&n_hits_sub, c.h_off + s1, 8, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(&n_regs_sub, c.r_off + s1, 8, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			if (n_regs_sub > al->cap_regs) { mmg_set_error("region arena overflow (%llu > regs_cap)", (unsigned long long)n_regs_sub); return MMG_ENOMEM; }
+			if (b->n_hits_dev + n_hits_sub > b->hits_cap) { mmg_set_error("result pool overflow (%llu hits)", (unsigned long long)(b->n_hits_dev + n_hits_sub)); return MMG_ENOMEM; }
+			STAGE_BEGIN();
+			launch_pack_hits(c, s0, s1, b->d_hits + b->n_hits_dev, al->n_sms, st);
+			CK(cudaMemcpyAsync(b->d_nregs + r0 + s0, c.n_regs + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToDevice, st));
+			STAGE_END(ST_REGS);
+			b->n_hits_dev += n_hits_sub;
+			b->dbg_r0 = r0 + s0, b->dbg_r1 = r0 + s1;
+			s0 = s1;
+		}
+		r0 = r1;
+	}
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	b->ran = true;
+	return MMG_OK;
+}
+
+int mmg_batch_fetch(mmg_aligner *al, mmg_batch *b)
+{
+	if (!b->ran) { mmg_set_error("batch not run"); return MMG_EINVAL; }
+	CK(cudaSetDevice(al->device));
+	cudaStream_t st = al->stream;
+	std::vector<uint32_t> nregs(b->n_reads + 1);
+	b->hits.resize(b->n_hits_dev);
+	STAGE_BEGIN();
+	if (b->n_reads) CK(cudaMemcpyAsync(nregs.data(), b->d_nregs, (size_t)b->n_reads * 4, cudaMemcpyDeviceToHost, st));
+	if (b->n_hits_dev) CK(cudaMemcpyAsync(b->hits.data(), b->d_hits, b->n_hits_dev * sizeof(mmg_hit_t), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(b->stats, b->d_stats, MMG_N_STATS * 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	STAGE_END(ST_D2H);
+	b->hit_off.resize(b->n_reads + 1);
+	uint64_t acc = 0;
+	for (uint32_t i = 0; i < b->n_reads; ++i) b->hit_off[i] = acc, acc += nregs[i];
+	b->hit_off[b->n_reads] = acc;
+	if (acc != b->n_hits_dev) { mmg_set_error("internal: hit count mismatch (%llu vs %llu)", (unsigned long long)acc, (unsigned long long)b->n_hits_dev); return MMG_ECUDA; }
+	b->fetched = true;
+	return MMG_OK;
+}
+
+int mmg_map_batch(mmg_aligner *al, const char *bases, const uint64_t *offsets, uint32_t n_reads, mmg_batch **out)
+{
+	int rc = mmg_batch_upload(al, bases, offsets, n_reads, out);
+	if (rc) return rc;
+	if ((rc = mmg_batch_run(al, *out)) || (rc = mmg_batch_fetch(al, *out))) { mmg_batch_destroy(*out); *out = 0; return rc; }
+	return MMG_OK;
+}
+
+void mmg_batch_destroy(mmg_batch *b)
+{
+	if (!b) return;
+	if (b->d_bases) cudaFree(b->d_bases);
+	if (b->d_off) cudaFree(b->d_off);
+	if (b->d_hits) cudaFree(b->d_hits);
+	if (b->d_nregs) cudaFree(b->d_nregs);
+	if (b->d_stats) cudaFree(b->d_stats);
+	delete b;
+}
+
+uint32_t mmg_batch_n_reads(const mmg_batch *b) { return b->n_reads; }
+uint64_t mmg_batch_n_hits(const mmg_batch *b) { return b->hits.size(); }
+const uint64_t *mmg_batch_hit_off(const mmg_batch *b) { return b->hit_off.data(); }
+const mmg_hit_t *mmg_batch_hits(const mmg_batch *b) { return b->hits.data(); }
+uint64_t mmg_batch_n_cigar(const mmg_batch *b) { return b->cigar.size(); }
+const uint32_t *mmg_batch_cigar(const mmg_batch *b) { return b->cigar.data(); }
+int mmg_batch_stats(const mmg_batch *b, uint64_t out[MMG_N_STATS]) { memcpy(out, b->stats, sizeof(b->stats)); return MMG_OK; }
+
+int mmg_stage_times(const mmg_aligner *al, double ms[MMG_N_STAGES], uint64_t launches[MMG_N_STAGES])
+{
+	memcpy(ms, al->stage_ms, sizeof(al->stage_ms));
+	memcpy(launches, al->stage_launches, sizeof(al->stage_launches));
+	return MMG_OK;
+}
+const char *mmg_stage_name(int s) { return s >= 0 && s < MMG_N_STAGES ? g_stage_names[s] : 0; }
+
+int64_t mmg_debug_dump(mmg_aligner *al, mmg_batch *b, int which, uint64_t *x, uint64_t *y, uint64_t cap, uint64_t *off)
+{
+	/* valid for the reads of the last processed sub-range only (tests use single-chunk batches) */
+	const ChunkDev &c = al->cd;
+	uint32_t n = b->dbg_r1 - b->dbg_r0;
+	if (b->dbg_r0 != 0 || n != b->n_reads) { mmg_set_error("debug dump needs a batch that fits one chunk"); return MMG_EINVAL; }
+	std::vector<uint32_t> cnt(n);
+	std::vector<uint64_t> aoff(n + 1);
+	if (cudaMemcpy(aoff.data(), c.a_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return MMG_ECUDA;
+	const uint32_t *dcnt = which == 0 ? c.n_mz : which == 1 ? c.n_a : which == 2 ? c.n_v : c.n_u;
+	if (cudaMemcpy(cnt.data(), dcnt, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return MMG_ECUDA;
+	uint64_t tot = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		off[i] = tot;
+		uint64_t src = which == 0 ? b->off[i] - b->off[0] : aoff[i] - aoff[0];
+		if (tot + cnt[i] <= cap && cnt[i]) {
+			if (which == 0) {
+				std::vector<uint32_t> y32(cnt[i]);
+				cudaMemcpy(x + tot, c.mz_x + src, (size_t)cnt[i] * 8, cudaMemcpyDeviceToHost);
+				cudaMemcpy(y32.data(), c.mz_y + src, (size_t)cnt[i] * 4, cudaMemcpyDeviceToHost);
+				for (uint32_t j = 0; j < cnt[i]; ++j) y[tot + j] = y32[j];
+			} else if (which == 1 || which == 2) {
+				cudaMemcpy(x + tot, c.bx + src, (size_t)cnt[i] * 8, cudaMemcpyDeviceToHost);
+				cudaMemcpy(y + tot, c.by + src, (size_t)cnt[i] * 8, cudaMemcpyDeviceToHost);
+			} else {
+				cudaMemcpy(x + tot, c.u + src, (size_t)cnt[i] * 8, cudaMemcpyDeviceToHost);
+			}
+		}
+		tot += cnt[i];
+	}
+	off[n] = tot;
+	return (int64_t)tot;
+}
+
+int mmg_batch_gen_cs(const mmg_aligner *, const mmg_batch *, uint64_t, char *, size_t) { mmg_set_error("cs needs CIGAR (not built yet)"); return MMG_EUNSUP; }
+int mmg_batch_gen_md(const mmg_aligner *, const mmg_batch *, uint64_t, char *, size_t) { mmg_set_error("MD needs CIGAR (not built yet)"); return MMG_EUNSUP; }
+
+const char *mmg_version(void)
+{
+#ifdef MMG_EMU
+	return "mmg 0.1 (SIMT-emulated test build)";
+#else
+	return "mmg 0.1 (sm_100a)";
+#endif
+}
+int mmg_sizeof_hit(void) { return (int)sizeof(mmg_hit_t); }
+
+} // extern "C"

@@ -1,0 +1,344 @@
+/* seed.cu -- query-side minimizer filter, index lookup, seed selection and
+ * anchor expansion (north-star (c), first half), one warp per read.
+ *
+ * Replaces, on the mm_map path (/root/reference/src/lib.rs:482,587; minimap2
+ * v2.26): seed.c mm_seed_mz_flt, mm_seed_collect_all (-> index.c mm_idx_get),
+ * mm_seed_select, mm_collect_matches and the expansion loop of map.c
+ * collect_seed_hits.  Anchors leave this file unsorted, in upstream's order
+ * (seed order, then the index's position order) because the downstream sort
+ * must reproduce radix_sort_128x's treatment of equal keys.
+ *
+ * Lookup: one 16-byte load per probe into the flat open-addressing table that
+ * replaces upstream's 2^b khash buckets; position runs are gathered with one
+ * lane per output anchor (load-balanced search over the seeds' prefix sums), so
+ * stores are coalesced even for high-occurrence seeds.
+ * Bound: HBM random access (32-byte sectors) - see DESIGN.md.
+ */
+#include "dev_common.cuh"
+#include "stages.h"
+
+#define SEED_NCNT 2048          /* query-occurrence counters per warp */
+#define MAX_MAX_HIGH_OCC 128    /* seed.c */
+
+__device__ __forceinline__ bool dev_idx_get(const DevIndex &di, uint64_t minier, uint32_t *n, uint64_t *val)
+{
+	const uint64_t m = ((uint64_t)1 << di.hbits) - 1;
+	uint64_t s = (minier * 0x9E3779B97F4A7C15ULL) >> (64 - di.hbits);
+	for (;;) {
+		mmg_u128 e = di.htab[s];
+		if (e.x == MMG_INF64) return false;
+		if (e.x >> 1 == minier) {
+			if (e.x & 1) *n = 1, *val = e.y;          /* the value is the position word itself */
+			else *n = (uint32_t)e.y, *val = e.y >> 32; /* offset into pos[] */
+			return true;
+		}
+		s = (s + 1) & m;
+	}
+}
+
+__device__ __forceinline__ void heap_down(uint64_t *l, int i, int n)
+{ /* ksort.h ks_heapdown: max-heap */
+	int k = i;
+	uint64_t tmp = l[i];
+	while ((k = (k << 1) + 1) < n) {
+		if (k != n - 1 && l[k] < l[k + 1]) ++k;
+		if (l[k] < tmp) break;
+		l[i] = l[k]; i = k;
+	}
+	l[i] = tmp;
+}
+
+/* seed.c: mm_seed_select, run by one lane (only reads with a high-occurrence seed get here) */
+__device__ void dev_seed_select(int n, const uint32_t *sn, const uint32_t *sq, uint32_t *meta, int len, int max_occ, int max_max_occ, int dist, uint64_t *b)
+{
+	if (n == 0 || n == 1) return;
+	for (int i = 0, last0 = -1; i <= n; ++i) {
+		if (i == n || (int)sn[i] <= max_occ) {
+			if (i - last0 > 1) {
+				int ps = last0 < 0 ? 0 : (int)(sq[last0] >> 1);
+				int pe = i == n ? len : (int)(sq[i] >> 1);
+				int j, k, st = last0 + 1, en = i;
+				int max_high_occ = (int)((double)(pe - ps) / dist + .499);
+				if (max_high_occ > 0) {
+					if (max_high_occ > MAX_MAX_HIGH_OCC) max_high_occ = MAX_MAX_HIGH_OCC;
+					for (j = st, k = 0; j < en && k < max_high_occ; ++j, ++k)
+						b[k] = (uint64_t)sn[j] << 32 | (uint32_t)j;
+					for (int h = (k >> 1) - 1; h >= 0; --h) heap_down(b, h, k);
+					for (; j < en; ++j) {
+						if (sn[j] < (uint32_t)(b[0] >> 32)) {
+							b[0] = (uint64_t)sn[j] << 32 | (uint32_t)j;
+							heap_down(b, 0, k);
+						}
+					}
+					for (j = 0; j < k; ++j) meta[(uint32_t)b[j]] |= 2u;
+				}
+				for (j = st; j < en; ++j) meta[j] ^= 2u;
+				for (j = st; j < en; ++j)
+					if ((int)sn[j] > max_max_occ) meta[j] |= 2u;
+			}
+			last0 = i;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(SEED_WARPS * 32)
+seed_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
+{
+	__shared__ uint32_t s_cnt[SEED_WARPS][SEED_NCNT];
+	__shared__ uint64_t s_heap[SEED_WARPS][MAX_MAX_HIGH_OCC];
+	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
+	const uint32_t lt = mmg_lanemask_lt();
+	unsigned long long tot_seed = 0, tot_hit = 0;
+
+	for (;;) {
+		uint32_t r = mmg_next_item(work);
+		if (r >= c.n_reads) break;
+		const uint64_t base = c.off[r] - c.off0;
+		const int qlen = (int)(c.off[r + 1] - c.off[r]);
+		int n = (int)c.n_mz[r];
+		uint64_t *mx = c.mz_x + base;
+		uint32_t *my = c.mz_y + base;
+
+		/* ---- mm_seed_mz_flt: drop minimizers that are too frequent IN THE QUERY ---- */
+		if (n > o.mid_occ && o.q_occ_frac > 0.0f && o.mid_occ > 0) {
+			uint32_t *cnt = s_cnt[wib];
+			for (int j = lane; j < SEED_NCNT; j += 32) cnt[j] = 0;
+			__syncwarp();
+			for (int i = lane; i < n; i += 32)
+				atomicAdd(&cnt[(uint32_t)((mx[i] * 0x9E3779B97F4A7C15ULL) >> 53)], 1u);
+			__syncwarp();
+			uint32_t mxc = 0;
+			for (int j = lane; j < SEED_NCNT; j += 32) mxc = max(mxc, cnt[j]);
+			mxc = __reduce_max_sync(MMG_FULL, mxc);
+			if ((int)mxc > o.mid_occ) { /* some key MAY exceed the threshold: count those exactly */
+				const float thr = (float)n * o.q_occ_frac;
+				int n_new = 0;
+				/* mark in sd_meta (free scratch at this point), then compact in order */
+				uint32_t *mark = c.sd_meta + base;
+				for (int i = lane; i < n; i += 32) {
+					uint64_t x = mx[i];
+					uint32_t d = 0;
+					if ((int)cnt[(uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> 53)] > o.mid_occ) {
+						int cn = 0;
+						for (int j = 0; j < n; ++j) cn += (mx[j] == x);
+						d = (cn > o.mid_occ && (float)cn > thr) ? 1u : 0u;
+					}
+					mark[i] = d;
+				}
+				__syncwarp();
+				for (int i0 = 0; i0 < n; i0 += 32) {
+					int i = i0 + lane;
+					bool keep = i < n && mark[i] == 0;
+					uint64_t x = i < n ? mx[i] : 0;
+					uint32_t y = i < n ? my[i] : 0;
+					uint32_t km = __ballot_sync(MMG_FULL, keep);
+					__syncwarp();
+					if (keep) { int d = n_new + __popc(km & lt); mx[d] = x, my[d] = y; }
+					n_new += __popc(km);
+					__syncwarp();
+				}
+				n = n_new;
+			}
+			__syncwarp();
+		}
+
+		/* ---- mm_seed_collect_all: index lookup, tandem flag, ordered compaction ---- */
+		uint64_t *sv = c.sd_val + base;
+		uint32_t *sn = c.sd_n + base, *sq = c.sd_qpos + base, *sm = c.sd_meta + base;
+		int n_m0 = 0, n_high = 0;
+		for (int i0 = 0; i0 < n; i0 += 32) {
+			int i = i0 + lane;
+			bool hit = false;
+			uint32_t hn = 0, meta = 0;
+			uint64_t hv = 0, x = 0;
+			if (i < n) {
+				x = mx[i];
+				hit = dev_idx_get(di, x >> 8, &hn, &hv);
+				if (hit) {
+					bool tandem = (i > 0 && mx[i - 1] >> 8 == x >> 8) || (i < n - 1 && mx[i + 1] >> 8 == x >> 8);
+					meta = (uint32_t)(x & 0xff) << 8 | (tandem ? 1u : 0u);
+				}
+			}
+			uint32_t hm = __ballot_sync(MMG_FULL, hit);
+			if (hit) {
+				int d = n_m0 + __popc(hm & lt);
+				sv[d] = hv, sn[d] = hn, sq[d] = my[i], sm[d] = meta;
+			}
+			n_m0 += __popc(hm);
+			n_high += __popc(__ballot_sync(MMG_FULL, hit && (int)hn > o.mid_occ));
+		}
+		__syncwarp();
+
+		/* ---- mm_seed_select / plain occurrence cut ---- */
+		if (n_high > 0) {
+			if (o.occ_dist > 0 && o.max_max_occ > o.mid_occ) {
+				if (lane == 0) dev_seed_select(n_m0, sn, sq, sm, qlen, o.mid_occ, o.max_max_occ, o.occ_dist, s_heap[wib]);
+			} else {
+				for (int i = lane; i < n_m0; i += 32) if ((int)sn[i] > o.mid_occ) sm[i] |= 2u;
+			}
+			__syncwarp();
+		}
+
+		/* ---- mm_collect_matches tail: rep_len, n_a, kept seeds ---- */
+		int n_m = n_m0, rep_len = 0;
+		unsigned long long n_a = 0;
+		if (n_high > 0) {
+			if (lane == 0) { /* serial: the interval union depends on order */
+				int rep_st = 0, rep_en = 0, k = 0;
+				for (int i = 0; i < n_m0; ++i) {
+					if (sm[i] & 2u) {
+						int en = (int)(sq[i] >> 1) + 1, st = en - (int)(sm[i] >> 8);
+						if (st > rep_en) { rep_len += rep_en - rep_st; rep_st = st, rep_en = en; }
+						else rep_en = en;
+					} else {
+						n_a += sn[i];
+						sv[k] = sv[i], sn[k] = sn[i], sq[k] = sq[i], sm[k] = sm[i];
+						++k;
+					}
+				}
+				rep_len += rep_en - rep_st;
+				n_m = k;
+			}
+			n_m = __shfl_sync(MMG_FULL, n_m, 0);
+			rep_len = __shfl_sync(MMG_FULL, rep_len, 0);
+			n_a = __shfl_sync(MMG_FULL, n_a, 0);
+		} else {
+			unsigned s = 0;
+			for (int i = lane; i < n_m0; i += 32) s += sn[i];
+			n_a = __reduce_add_sync(MMG_FULL, s);
+		}
+		if (lane == 0) {
+			c.n_mz[r] = (uint32_t)n;
+			c.n_seed[r] = (uint32_t)n_m;
+			c.n_a[r] = (uint32_t)n_a;
+			c.rep_len[r] = rep_len;
+		}
+		tot_seed += n_m, tot_hit += n_a;
+		__syncwarp();
+	}
+	if (lane == 0 && (tot_seed | tot_hit)) {
+		atomicAdd(&c.stats[2], tot_seed);
+		atomicAdd(&c.stats[3], tot_hit);
+	}
+}
+
+/* ---- anchor expansion: map.c collect_seed_hits inner loops ---------------- */
+__global__ void __launch_bounds__(SEED_WARPS * 32)
+expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
+{
+	const int lane = mmg_lane();
+	for (;;) {
+		uint32_t r = r0 + mmg_next_item(work);
+		if (r >= r1) break;
+		const uint64_t base = c.off[r] - c.off0;
+		const int qlen = (int)(c.off[r + 1] - c.off[r]);
+		const int n_m = (int)c.n_seed[r];
+		const uint64_t *sv = c.sd_val + base;
+		const uint32_t *sn = c.sd_n + base, *sq = c.sd_qpos + base, *sm = c.sd_meta + base;
+		uint64_t *ax = c.ax + (c.a_off[r] - c.a_off0), *ay = c.ay + (c.a_off[r] - c.a_off0);
+		uint32_t out = 0;
+		for (int i0 = 0; i0 < n_m; i0 += 32) {
+			int i = i0 + lane;
+			int cnt = i < n_m ? (int)sn[i] : 0, tot;
+			uint64_t val = i < n_m ? sv[i] : 0;
+			uint32_t qp = i < n_m ? sq[i] : 0, meta = i < n_m ? sm[i] : 0;
+			int ex = mmg_warp_excl_scan(cnt, &tot);
+			for (int t0 = 0; t0 < tot; t0 += 32) {
+				int t = t0 + lane;
+				/* find the seed that owns output t: largest lane s with ex[s] <= t (ex is non-decreasing) */
+				int s = 0;
+#pragma unroll
+				for (int d = 16; d; d >>= 1) {
+					int cand = s + d;
+					int exc = __shfl_sync(MMG_FULL, ex, cand & 31);
+					if (cand < 32 && exc <= t) s = cand;
+				}
+				/* skip empty seeds that share the same prefix: the owner is the last lane with ex<=t and cnt>0;
+				 * the binary search lands on the last lane with ex <= t, which has cnt > 0 whenever t < tot */
+				int s_ex = __shfl_sync(MMG_FULL, ex, s);
+				int s_cnt = __shfl_sync(MMG_FULL, cnt, s);
+				uint64_t s_val = __shfl_sync(MMG_FULL, val, s);
+				uint32_t s_qp = __shfl_sync(MMG_FULL, qp, s), s_meta = __shfl_sync(MMG_FULL, meta, s);
+				if (t < tot) {
+					int kk = t - s_ex;
+					uint64_t rr = s_cnt == 1 ? s_val : di.pos[s_val + kk];
+					uint32_t rpos = (uint32_t)rr >> 1, span = s_meta >> 8;
+					uint64_t x, y;
+					if ((rr & 1) == (s_qp & 1)) { /* forward strand */
+						x = (rr & 0xffffffff00000000ULL) | rpos;
+						y = (uint64_t)span << 32 | (s_qp >> 1);
+					} else {
+						x = 1ULL << 63 | (rr & 0xffffffff00000000ULL) | rpos;
+						y = (uint64_t)span << 32 | (uint32_t)(qlen - (int)((s_qp >> 1) + 1 - span) - 1);
+					}
+					if (s_meta & 1u) y |= 1ULL << 42; /* MM_SEED_TANDEM */
+					ax[out + t] = x, ay[out + t] = y;
+				}
+			}
+			out += tot;
+		}
+		__syncwarp();
+	}
+}
+
+/* ---- exclusive scan of per-read counts (single block; n is a few 10^5) ---- */
+__global__ void __launch_bounds__(1024)
+scan_u32_kernel(const uint32_t *in, uint64_t *out, uint32_t n)
+{
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_carry;
+	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	for (uint32_t i0 = 0; i0 < n; i0 += 1024) {
+		uint32_t i = i0 + threadIdx.x;
+		unsigned long long v = i < n ? in[i] : 0, x = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			unsigned long long y = __shfl_up_sync(MMG_FULL, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31) s_warp[wib] = x;
+		__syncthreads();
+		if (wib == 0) {
+			unsigned long long w = s_warp[lane], ws = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				unsigned long long y = __shfl_up_sync(MMG_FULL, ws, o);
+				if (lane >= o) ws += y;
+			}
+			s_warp[lane] = ws - w;
+		}
+		__syncthreads();
+		unsigned long long carry = s_carry;
+		if (i < n) out[i] = carry + s_warp[wib] + x - v;
+		__syncthreads();
+		if (threadIdx.x == 1023) s_carry = carry + s_warp[wib] + x;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+int launch_seed(const ChunkDev &c, const DevIndex &di, const DevOpt &o, int n_sms, cudaStream_t st, uint32_t *work)
+{
+	int grid = n_sms * 4, need = ((int)c.n_reads + SEED_WARPS - 1) / SEED_WARPS;
+	if (grid > need) grid = need;
+	if (grid < 1) grid = 1;
+	MMG_LAUNCH(seed_kernel, grid, SEED_WARPS * 32, 0, st, c, di, o, work);
+	return 0;
+}
+
+int launch_expand(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work)
+{
+	int grid = n_sms * 8, need = ((int)(r1 - r0) + SEED_WARPS - 1) / SEED_WARPS;
+	if (grid > need) grid = need;
+	if (grid < 1) grid = 1;
+	MMG_LAUNCH(expand_kernel, grid, SEED_WARPS * 32, 0, st, c, di, o, r0, r1, work);
+	return 0;
+}
+
+int launch_scan_u32(const uint32_t *in, uint64_t *out, uint32_t n, cudaStream_t st)
+{
+	MMG_LAUNCH(scan_u32_kernel, 1, 1024, 0, st, in, out, n);
+	return 0;
+}

@@ -1,0 +1,25 @@
+/* stages.h -- host launchers of the stage kernels (one .cu per stage). */
+#ifndef MMG_STAGES_H
+#define MMG_STAGES_H
+#include "dev_common.cuh"
+
+#define SKETCH_WARPS 8
+#define SEED_WARPS 8
+#define CHAIN_WARPS 4
+#define SORT_THREADS 256
+#define SORT_SMEM_ELEMS 8192
+
+enum { ST_H2D = 0, ST_SKETCH, ST_SEED, ST_SCAN, ST_EXPAND, ST_SORT, ST_CHAIN, ST_BACKTRACK, ST_RECHAIN, ST_REGS, ST_EXTEND, ST_D2H };
+
+int launch_sketch(const ChunkDev &c, const DevIndex &di, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_seed(const ChunkDev &c, const DevIndex &di, const DevOpt &o, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_scan_u32(const uint32_t *in, uint64_t *out, uint32_t n, cudaStream_t st);  /* out[n] = total */
+int launch_expand(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_sort(const ChunkDev &c, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_chain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_backtrack(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_rechain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_regs(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32_t r0, uint32_t r1, uint64_t regs_cap, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_pack_hits(const ChunkDev &c, uint32_t r0, uint32_t r1, mmg_hit_t *hits, int n_sms, cudaStream_t st);
+
+#endif
