@@ -195,11 +195,16 @@ int mmg_batch_stats(const mmg_batch *b, uint64_t out[MMG_N_STATS]);
 #define MMG_N_STAGES 12
 int mmg_stage_times(const mmg_aligner *al, double ms[MMG_N_STAGES], uint64_t launches[MMG_N_STAGES]);
 const char *mmg_stage_name(int stage);
+/* device milliseconds of the last mmg_batch_run: CUDA events on the library's stream around all its kernels */
+double mmg_last_run_ms(const mmg_aligner *al);
 
 /* intermediate device arrays of one batch, copied to the host (differential
  * tests): which = 0 minimizers (x,y), 1 sorted anchors (x,y), 2 chained anchors
  * (x,y), 3 chains u[]; per-read offsets in `off` (n_reads+1). Returns count. */
 int64_t mmg_debug_dump(mmg_aligner *al, mmg_batch *b, int which, uint64_t *x, uint64_t *y, uint64_t cap, uint64_t *off);
+
+/* test hook: the device logf used by the mapq computation, over an array */
+int mmg_debug_logf(const float *x, float *y, uint64_t n);
 
 const char *mmg_last_error(void);
 const char *mmg_version(void);

@@ -37,7 +37,8 @@ struct mmg_aligner {
 	int profile;
 	double stage_ms[MMG_N_STAGES];
 	uint64_t stage_launches[MMG_N_STAGES];
-	cudaEvent_t ev0, ev1;
+	cudaEvent_t ev0, ev1, ev_run0, ev_run1;
+	double last_run_ms;
 };
 
 struct mmg_batch {
@@ -160,6 +161,9 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	CK(cudaStreamCreateWithFlags(&al->stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&al->ev0));
 	CK(cudaEventCreate(&al->ev1));
+	CK(cudaEventCreate(&al->ev_run0));
+	CK(cudaEventCreate(&al->ev_run1));
+	al->last_run_ms = 0;
 	al->arenas_ready = false;
 	al->profile = 0;
 	al->cap_bases = (uint64_t)96 << 20, al->cap_reads = 1u << 17, al->cap_anchors = (uint64_t)48 << 20, al->cap_regs = (uint64_t)4 << 20;
@@ -180,6 +184,8 @@ void mmg_aligner_destroy(mmg_aligner *al)
 	if (al->stream) cudaStreamDestroy(al->stream);
 	if (al->ev0) cudaEventDestroy(al->ev0);
 	if (al->ev1) cudaEventDestroy(al->ev1);
+	if (al->ev_run0) cudaEventDestroy(al->ev_run0);
+	if (al->ev_run1) cudaEventDestroy(al->ev_run1);
 	delete al;
 }
 
@@ -247,6 +253,7 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 	memset(al->stage_ms, 0, sizeof(al->stage_ms));
 	memset(al->stage_launches, 0, sizeof(al->stage_launches));
 	b->n_hits_dev = 0;
+	CK(cudaEventRecord(al->ev_run0, st));
 	const uint32_t n = b->n_reads;
 	std::vector<uint64_t> h_aoff;
 	for (uint32_t r0 = 0; r0 < n;) {
@@ -303,8 +310,10 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 		}
 		r0 = r1;
 	}
+	CK(cudaEventRecord(al->ev_run1, st));
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
+	{ float ms = 0; cudaEventElapsedTime(&ms, al->ev_run0, al->ev_run1); al->last_run_ms = ms; }
 	b->ran = true;
 	return MMG_OK;
 }
@@ -364,6 +373,7 @@ int mmg_stage_times(const mmg_aligner *al, double ms[MMG_N_STAGES], uint64_t lau
 	memcpy(launches, al->stage_launches, sizeof(al->stage_launches));
 	return MMG_OK;
 }
+double mmg_last_run_ms(const mmg_aligner *al) { return al->last_run_ms; }
 const char *mmg_stage_name(int s) { return s >= 0 && s < MMG_N_STAGES ? g_stage_names[s] : 0; }
 
 int64_t mmg_debug_dump(mmg_aligner *al, mmg_batch *b, int which, uint64_t *x, uint64_t *y, uint64_t cap, uint64_t *off)

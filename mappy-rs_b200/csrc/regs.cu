@@ -92,6 +92,25 @@ pack_hits_kernel(ChunkDev c, uint32_t r0, uint32_t r1, mmg_hit_t *hits)
 	}
 }
 
+/* test hook: dev_logf over an array (the mapq path's only transcendental) */
+__global__ void logf_kernel(const float *x, float *y, uint64_t n)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) y[i] = dev_logf(x[i]);
+}
+
+extern "C" int mmg_debug_logf(const float *x, float *y, uint64_t n)
+{
+	float *dx = 0, *dy = 0;
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return MMG_ENODEV;
+	if (cudaMalloc((void**)&dx, n * 4) != cudaSuccess || cudaMalloc((void**)&dy, n * 4) != cudaSuccess) return MMG_ENOMEM;
+	cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice);
+	MMG_LAUNCH(logf_kernel, 64, 256, 0, (cudaStream_t)0, (const float*)dx, dy, n);
+	cudaError_t e = cudaMemcpy(y, dy, n * 4, cudaMemcpyDeviceToHost);
+	cudaFree(dx); cudaFree(dy);
+	return e == cudaSuccess ? MMG_OK : MMG_ECUDA;
+}
+
 int launch_regs(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32_t r0, uint32_t r1, uint64_t regs_cap, int n_sms, cudaStream_t st, uint32_t *work)
 {
 	int grid = n_sms * 12, need = ((int)(r1 - r0) + CHAIN_WARPS - 1) / CHAIN_WARPS;

@@ -17,7 +17,7 @@
 #include "dev_common.cuh"
 #include "stages.h"
 
-#define SEED_NCNT 2048          /* query-occurrence counters per warp */
+#define SEED_NCNT 1024          /* query-occurrence counters per warp */
 #define MAX_MAX_HIGH_OCC 128    /* seed.c */
 
 __device__ __forceinline__ bool dev_idx_get(const DevIndex &di, uint64_t minier, uint32_t *n, uint64_t *val)
@@ -105,7 +105,7 @@ seed_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 			for (int j = lane; j < SEED_NCNT; j += 32) cnt[j] = 0;
 			__syncwarp();
 			for (int i = lane; i < n; i += 32)
-				atomicAdd(&cnt[(uint32_t)((mx[i] * 0x9E3779B97F4A7C15ULL) >> 53)], 1u);
+				atomicAdd(&cnt[(uint32_t)((mx[i] * 0x9E3779B97F4A7C15ULL) >> 54)], 1u);
 			__syncwarp();
 			uint32_t mxc = 0;
 			for (int j = lane; j < SEED_NCNT; j += 32) mxc = max(mxc, cnt[j]);
@@ -118,7 +118,7 @@ seed_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 				for (int i = lane; i < n; i += 32) {
 					uint64_t x = mx[i];
 					uint32_t d = 0;
-					if ((int)cnt[(uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> 53)] > o.mid_occ) {
+					if ((int)cnt[(uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> 54)] > o.mid_occ) {
 						int cn = 0;
 						for (int j = 0; j < n; ++j) cn += (mx[j] == x);
 						d = (cn > o.mid_occ && (float)cn > thr) ? 1u : 0u;

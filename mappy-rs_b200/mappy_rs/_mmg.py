@@ -60,7 +60,7 @@ EXPORTS = ["mmg_set_opt", "mmg_mapopt_update", "mmg_index_open", "mmg_index_buil
            "mmg_batch_upload", "mmg_batch_run", "mmg_batch_fetch", "mmg_batch_n_reads", "mmg_batch_n_hits",
            "mmg_batch_hit_off", "mmg_batch_hits", "mmg_batch_n_cigar", "mmg_batch_cigar", "mmg_batch_gen_cs",
            "mmg_batch_gen_md", "mmg_batch_destroy", "mmg_batch_stats", "mmg_stage_times", "mmg_stage_name",
-           "mmg_debug_dump", "mmg_last_error", "mmg_version", "mmg_sizeof_hit"]
+           "mmg_last_run_ms", "mmg_debug_dump", "mmg_last_error", "mmg_version", "mmg_sizeof_hit"]
 
 
 class MmgError(RuntimeError):
@@ -108,6 +108,7 @@ class Lib:
         L.mmg_batch_stats.argtypes = [c_vp, c_vp]
         L.mmg_stage_times.argtypes = [c_vp, c_vp, c_vp]
         L.mmg_stage_name.restype = c_cp; L.mmg_stage_name.argtypes = [c_int]
+        L.mmg_last_run_ms.restype = ctypes.c_double; L.mmg_last_run_ms.argtypes = [c_vp]
         L.mmg_debug_dump.restype = c_i64; L.mmg_debug_dump.argtypes = [c_vp, c_vp, c_int, c_vp, c_vp, c_u64, c_vp]
         L.mmg_last_error.restype = c_cp
         L.mmg_version.restype = c_cp
@@ -233,6 +234,8 @@ class DeviceAligner:
     def run(self, b): self.lib.check(self.lib.L.mmg_batch_run(self.h, b))
     def fetch(self, b): self.lib.check(self.lib.L.mmg_batch_fetch(self.h, b))
     def free(self, b): self.lib.L.mmg_batch_destroy(b)
+
+    def last_run_ms(self): return float(self.lib.L.mmg_last_run_ms(self.h))
 
     def stage_times(self):
         ms = np.zeros(N_STAGES, dtype=np.float64); ln = np.zeros(N_STAGES, dtype=np.uint64)

@@ -1,0 +1,101 @@
+"""Kernel-source parity on CPU: the product's .cu files compiled against the
+test-only SIMT emulator (tests/emu) and compared with the oracle, hit for hit
+and stage for stage.  Small inputs (the emulator runs ~10^2-10^3 reads/s); the
+same cases at full size are the `gpu` tests."""
+import os
+
+import numpy as np
+import pytest
+
+import data_gen
+import parity
+from conftest import GOLDEN
+
+MMI = os.path.join(GOLDEN, "test.mmi")
+
+
+@pytest.fixture(scope="module")
+def plain_case(emu_lib, oracle_mod):
+    ref, coff, names, seqs = parity.random_reference(11, [150000, 60000])
+    c = parity.Case(emu_lib, names, seqs)
+    c.ref, c.coff = ref, coff
+    yield c
+    c.close()
+
+
+def test_mapping_only_reads(plain_case):
+    buf, offs, _ = data_gen.make_reads(12, plain_case.ref, plain_case.coff, 300, 300, 5000)
+    dev, stage_diffs = parity.compare_stages(plain_case, buf, offs, max_reads=60)
+    ora = plain_case.oracle.map_batch(buf, offs, 4)
+    assert stage_diffs == []
+    assert parity.compare_stats(dev, ora) == []
+    assert parity.compare_hits(dev, ora) == []
+    assert len(dev.hits) >= 290
+
+
+def test_edge_case_reads(plain_case):
+    """SURVEY.md appendix D edge corpus: short reads, N runs, homopolymers, palindromes, empty read."""
+    ref = plain_case.ref
+    rs = np.random.RandomState(5)
+    base = ref[1000:3000].tobytes().decode()
+    reads = [
+        "", "A", "ACGT", base[:14], base[:15], base[:24], base[:25], base[:40],
+        "N" * 50, base[:300] + "N" * 7 + base[300:900], "".join(c if i % 10 else "N" for i, c in enumerate(base[:1200])),
+        "A" * 600, "AT" * 300, "ACGT" * 200, base[:500] + "A" * 300 + base[500:1000],
+        base[:700].lower(), base[100:900][::-1], "ACGTTGCA" * 60 + base[:400] + "TGCAACGT" * 40,
+        base[:800] + ref[50000:50800].tobytes().decode(), "".join(rs.choice(list("ACGT"), 2000)),
+        base, base[:1000] + "NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN" + base[1000:],
+    ]
+    buf, offs = plain_case.oracle and __import__("mm2oracle").pack_reads(reads)
+    dev, stage_diffs = parity.compare_stages(plain_case, buf, offs)
+    ora = plain_case.oracle.map_batch(buf, offs, 1)
+    assert stage_diffs == []
+    assert parity.compare_stats(dev, ora) == []
+    assert parity.compare_hits(dev, ora) == []
+
+
+def test_reference_fixture_reads(emu_lib, oracle_mod):
+    """The reference's own workload: the 4 contigs of test.fa mapped to test.mmi (tests/python_test.py:167-178)."""
+    c = parity.Case(emu_lib, None, None, mmi=MMI)
+    try:
+        seqs = [c.oracle.seq(n) for n in c.oracle.seq_names] * 3
+        buf, offs = oracle_mod.pack_reads(seqs)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 1)
+        assert parity.compare_hits(dev, ora) == []
+        assert len(dev.hits) == 12 and set(dev.hits["mapq"].tolist()) == {60}
+    finally:
+        c.close()
+
+
+def test_hifi_preset(emu_lib, oracle_mod):
+    ref, coff, names, seqs = parity.random_reference(21, [120000])
+    c = parity.Case(emu_lib, names, seqs, preset="map-hifi")
+    try:
+        buf, offs, _ = data_gen.make_reads(22, ref, coff, 60, 2000, 9000, p_sub=0.002, p_ins=0.0015, p_del=0.0015)
+        dev, stage_diffs = parity.compare_stages(c, buf, offs, max_reads=30)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert stage_diffs == [] and parity.compare_hits(dev, ora) == []
+    finally:
+        c.close()
+
+
+def test_multi_chunk_equals_single_chunk(emu_lib, oracle_mod):
+    """Small arenas force several chunks and anchor sub-ranges; results must not change."""
+    ref, coff, names, seqs = parity.random_reference(31, [80000])
+    c = parity.Case(emu_lib, names, seqs)
+    try:
+        c.aligner.set("chunk_bases", 20000)
+        c.aligner.set("chunk_reads", 16)
+        c.aligner.set("anchor_cap", 3000)
+        buf, offs, _ = data_gen.make_reads(32, ref, coff, 120, 300, 4000)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_hits(dev, ora) == [] and parity.compare_stats(dev, ora) == []
+    finally:
+        c.close()
+
+
+def test_device_logf_source_matches_host_libm(emu_lib):
+    """The glibc-logf restatement in regs.cu (tables typed into the product source) vs the host libm."""
+    assert parity.logf_mismatches(emu_lib, 100000) == 0

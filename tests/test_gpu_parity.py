@@ -1,0 +1,108 @@
+"""Parity tests proper: the product library (nvcc, sm_100a) on a real B200 through
+the C ABI, against the oracle on the same seeded inputs.  Bit-exact on every hit
+field; stage dumps attribute a mismatch to a kernel."""
+import os
+
+import numpy as np
+import pytest
+
+import data_gen
+import parity
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+MMI = os.path.join(GOLDEN, "test.mmi")
+
+
+@pytest.fixture(scope="module")
+def case5mb(gpu_lib, oracle_mod):
+    """BASELINE.json configs[1]: 5 Mb random reference, map-ont, mapping-only."""
+    ref, coff, names = data_gen.config1_reference()
+    seqs = [ref.tobytes()]
+    c = parity.Case(gpu_lib, names, seqs)
+    c.ref, c.coff = ref, coff
+    yield c
+    c.close()
+
+
+def test_native_library_is_loaded(gpu_lib):
+    assert "sm_100a" in gpu_lib.version()
+    assert gpu_lib.path.endswith("mappy-rs_b200/libmmg.so")
+
+
+def test_config1_sample_bit_exact(case5mb):
+    buf, offs, _ = data_gen.config1_reads(case5mb.ref, case5mb.coff, 20000)
+    dev = case5mb.aligner.map_batch(buf, offs)
+    ora = case5mb.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+    assert parity.compare_stats(dev, ora) == []
+    assert parity.compare_hits(dev, ora) == []
+    assert len(dev.hits) >= 19900
+
+
+def test_config1_stages(case5mb):
+    buf, offs, _ = data_gen.make_reads(77, case5mb.ref, case5mb.coff, 2000, 1000, 10000)
+    dev, diffs = parity.compare_stages(case5mb, buf, offs, max_reads=400)
+    assert diffs == []
+
+
+def test_edge_case_reads(case5mb, oracle_mod):
+    ref = case5mb.ref
+    rs = np.random.RandomState(5)
+    base = ref[1000:4000].tobytes().decode()
+    reads = [
+        "", "A", "ACGT", base[:14], base[:15], base[:24], base[:25], base[:40],
+        "N" * 50, base[:300] + "N" * 7 + base[300:900], "".join(c if i % 10 else "N" for i, c in enumerate(base[:1200])),
+        "A" * 600, "AT" * 300, "ACGT" * 200, base[:500] + "A" * 300 + base[500:1000],
+        base[:700].lower(), base[100:900][::-1], "ACGTTGCA" * 60 + base[:400] + "TGCAACGT" * 40,
+        base[:800] + ref[50000:50800].tobytes().decode(), "".join(rs.choice(list("ACGT"), 2000)),
+        base, base[:1000] + "N" * 32 + base[1000:], ref[200000:260000].tobytes().decode(),
+    ]
+    buf, offs = oracle_mod.pack_reads(reads)
+    dev, diffs = parity.compare_stages(case5mb, buf, offs)
+    ora = case5mb.oracle.map_batch(buf, offs, 1)
+    assert diffs == []
+    assert parity.compare_hits(dev, ora) == []
+
+
+def test_reference_fixture(gpu_lib, oracle_mod):
+    c = parity.Case(gpu_lib, None, None, mmi=MMI)
+    try:
+        seqs = [c.oracle.seq(n) for n in c.oracle.seq_names] * 10
+        buf, offs = oracle_mod.pack_reads(seqs)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 1)
+        assert parity.compare_hits(dev, ora) == [] and len(dev.hits) == 40
+    finally:
+        c.close()
+
+
+def test_hifi_preset(gpu_lib, oracle_mod):
+    ref, coff, names, seqs = parity.random_reference(21, [2000000])
+    c = parity.Case(gpu_lib, names, seqs, preset="map-hifi")
+    try:
+        buf, offs, _ = data_gen.make_reads(22, ref, coff, 2000, 10000, 25000, len_mean=15000, len_sd=2000, p_sub=0.002, p_ins=0.0015, p_del=0.0015)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+        assert parity.compare_hits(dev, ora) == [] and parity.compare_stats(dev, ora) == []
+    finally:
+        c.close()
+
+
+def test_multi_chunk_equals_oracle(gpu_lib, oracle_mod):
+    ref, coff, names, seqs = parity.random_reference(31, [1000000])
+    c = parity.Case(gpu_lib, names, seqs)
+    try:
+        c.aligner.set("chunk_bases", 2_000_000)
+        c.aligner.set("chunk_reads", 512)
+        c.aligner.set("anchor_cap", 150_000)
+        buf, offs, _ = data_gen.make_reads(32, ref, coff, 5000, 300, 8000)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+        assert parity.compare_hits(dev, ora) == [] and parity.compare_stats(dev, ora) == []
+    finally:
+        c.close()
+
+
+def test_device_logf_matches_host_libm(gpu_lib):
+    """mapq uses logf(); the device restatement of glibc's algorithm is compared with the host libm."""
+    assert parity.logf_mismatches(gpu_lib, 300000) == 0

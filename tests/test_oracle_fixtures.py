@@ -1,0 +1,85 @@
+"""The oracle against every fixture the reference's own tests hold for this path
+(SURVEY.md section 8c): resources/test/test.{fa,mmi} copied to tests/golden/ and
+the assertions of /root/reference/src/lib.rs:1040-1106 and tests/python_test.py."""
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+
+MMI = os.path.join(GOLDEN, "test.mmi")
+FA = os.path.join(GOLDEN, "test.fa")
+
+ENTEROCOCCUS = (
+    "AGAGCAGGTAGGATCGTTGAAAAAAGAGTACTCAGGATTCCATTCAACTTTTACTGATTTGAAGCGTACTGTTTATGGCC"
+    "AAGAATATTTACGTCTTTACAACCAATACGCAAAAAAAGGTTCATTGAGTTTGGTTGTGATTTGATGAAAATTACTGAGA"
+    "ATAACAGGATTATTAAGCTGATTGATGAACTAAATCAGCTTAATAAATATTCTTTGCAGATAGGAATATTTGGGGAAAAT"
+    "GATTCTTTTATGGCGATGTTGGCCCAAGTTCATGAATTTGGGGTGACTATTCGTCCCAAAGGTCGTTTTCTTGTTATACC"
+    "ACTTATGAAAAAGTATAGAGGTAAAAGTCCACGTCAATTTGATTTGTTTTTTATGCAAACTAAAGAAAATCACAAGTTTT")
+BACILLUS = (
+    "AGAGTGAAGCCAATATTCCGATAACGATTGCTTTCATGATATCCCTCATTCTGGCATTATTTTTTTATACTATACTATTC"
+    "GATATCGCACAGATCAATGGAGTCGTGAGAAAATAAACATGTTTTGCGAACCGCTATGTGTGGAAGACAAAAAATGGAGG"
+    "TGAAATTGATGGAAGCAAAGACACAGGCGTACTTTTTTCAGGATGATGGCAGGATTCCGAATCACCCTGATTTTCCGCTC"
+    "GTTGTGTATCAAAACGCACTCAAGGACACCGGTCAGGCAGAGCGGATCGTCAACCGGCATGGCTGGTCAAACAGCTGGTC"
+    "GGGGAGTGTTTTTCCATACCATCATTATCACAGCAATACGCATGAAGTCCTGATTGCAGTTCGGGGAGAGGCTGTGATTC")
+
+
+def read_fasta(path):
+    out, name = [], None
+    for line in open(path):
+        line = line.strip()
+        if line.startswith(">"):
+            name = line[1:].split()[0]
+            out.append([name, ""])
+        elif line:
+            out[-1][1] += line
+    return out
+
+
+def test_index_properties(oracle_mod):
+    o = oracle_mod.Oracle(MMI)
+    assert (o.k, o.w, o.n_seq) == (15, 10, 4)            # src/lib.rs:1046-1061
+    assert sorted(o.seq_names) == ["Bacillus_subtilis", "Enterococcus_faecalis", "Escherichia_coli_1", "Escherichia_coli_2"]
+    assert o.seq("Bacillus_subtilis") == BACILLUS         # src/lib.rs:1078-1091
+    assert o.get_opt("mid_occ") == 10
+
+
+def test_mmi_equals_index_built_from_fasta(oracle_mod):
+    """hash64 + mm_sketch + bucket/key split: all 280 entries of test.mmi are rebuilt from test.fa."""
+    a = oracle_mod.Oracle(MMI).index_entries()
+    b = oracle_mod.Oracle(FA).index_entries()
+    sa = sorted(zip(a[0].tolist(), a[1].tolist()))
+    sb = sorted(zip(b[0].tolist(), b[1].tolist()))
+    assert len(sa) == 280 and sa == sb
+
+
+def test_mmi_roundtrip_bytes(oracle_mod, tmp_path):
+    """mm_idx_dump of the loaded index reproduces the file except for khash slot order."""
+    o = oracle_mod.Oracle(MMI)
+    out = tmp_path / "o.mmi"
+    o.dump_index(out)
+    assert os.path.getsize(out) == os.path.getsize(MMI) == 136470
+    o2 = oracle_mod.Oracle(str(out))
+    a, b = o.index_entries(), o2.index_entries()
+    assert np.array_equal(np.sort(a[0]), np.sort(b[0])) and o2.seq("Bacillus_subtilis") == BACILLUS
+
+
+def test_sketch_of_contigs_matches_mmi(oracle_mod):
+    o = oracle_mod.Oracle(MMI)
+    mz, y = o.index_entries()
+    want = set(zip(mz.tolist(), y.tolist()))
+    got = set()
+    for rid, (name, seq) in enumerate(read_fasta(FA)):
+        x, yy = oracle_mod.sketch(seq, 10, 15, rid=rid)
+        got |= set(zip((x >> np.uint64(8)).tolist(), yy.tolist()))
+    assert got == want
+
+
+def test_map_one_mapping_only(oracle_mod):
+    """Chain-level coordinates predicted in SURVEY.md appendix E (no CIGAR): 1..394, 75 anchors, score 393."""
+    o = oracle_mod.Oracle(MMI)
+    o.set_opt("flag", 0)
+    r = o.map(ENTEROCOCCUS)
+    assert len(r.hits) == 1
+    h = r.hits[0]
+    assert (h["rid"], h["rs"], h["re"], h["qs"], h["qe"], h["cnt"], h["score"], h["mapq"], h["rev"]) == (1, 1, 394, 1, 394, 75, 393, 60, 0)
