@@ -253,6 +253,7 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 	memset(al->stage_ms, 0, sizeof(al->stage_ms));
 	memset(al->stage_launches, 0, sizeof(al->stage_launches));
 	b->n_hits_dev = 0;
+	CK(cudaMemsetAsync(b->d_stats, 0, MMG_N_STATS * 8, st));
 	CK(cudaEventRecord(al->ev_run0, st));
 	const uint32_t n = b->n_reads;
 	std::vector<uint64_t> h_aoff;
