@@ -34,6 +34,7 @@ struct mmg_aligner {
 	uint32_t cap_reads;
 	bool arenas_ready;
 	ChunkDev cd;                       /* arena pointers */
+	unsigned char *rmq_nodes;          /* AVL node arena of the re-chain stage */
 	int profile;
 	double stage_ms[MMG_N_STAGES];
 	uint64_t stage_launches[MMG_N_STAGES];
@@ -132,6 +133,7 @@ static int alloc_arenas(mmg_aligner *al)
 	AL(c.n_u, R); AL(c.n_v, R); AL(c.r_off, R + 1);
 	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
 	AL(c.work, 64); AL(c.flags, R);
+	AL(al->rmq_nodes, (2 * A + 2 * R + 2) * RMQ_NODE_BYTES);
 #undef AL
 	al->arenas_ready = true;
 	return MMG_OK;
@@ -287,7 +289,7 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 			STAGE_BEGIN(); launch_sort(c, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_SORT);
 			STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
 			STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
-			STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);
+			STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);
 			STAGE_BEGIN();
 			launch_scan_u32(c.n_u + s0, c.r_off + s0, s1 - s0, st);
 			STAGE_END(ST_SCAN);

@@ -18,7 +18,8 @@ int launch_expand(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32
 int launch_sort(const ChunkDev &c, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_chain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_backtrack(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
-int launch_rechain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+#define RMQ_NODE_BYTES 40 /* sizeof(RNode) in rmq.cu; the arena holds 2 * (anchors + reads) nodes */
+int launch_rechain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, void *nodes, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_regs(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32_t r0, uint32_t r1, uint64_t regs_cap, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_pack_hits(const ChunkDev &c, uint32_t r0, uint32_t r1, mmg_hit_t *hits, int n_sms, cudaStream_t st);
 

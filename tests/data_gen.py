@@ -94,3 +94,34 @@ def config1_reads(ref, coff, n_reads=200_000):
 def config2_contig_lens(total=3_100_000_000):
     s = float(sum(GRCH38_LENS))
     return [int(round(x / s * total)) for x in GRCH38_LENS]
+
+
+def make_sv_reads(seed, ref, coff, n_reads, len_min=400, len_max=4000):
+    """Reads that exercise multi-chain logic: plain reads, chimeras (two loci), reads with a 0.6-4 kb
+    deletion or insertion relative to the reference (broken chains -> RMQ long-join re-chaining)."""
+    rs = np.random.RandomState(seed)
+    base_buf, base_offs, _ = make_reads(seed + 7, ref, coff, n_reads * 2, len_min, len_max)
+    reads = reads_as_list(base_buf, base_offs)
+    comp = str.maketrans("ACGT", "TGCA")
+    out = []
+    n_ctg = len(coff) - 1
+    for i in range(n_reads):
+        kind = rs.randint(4)
+        c = rs.randint(n_ctg)
+        c0, L = int(coff[c]), int(coff[c + 1] - coff[c])
+        if kind == 0 or L < 14000:
+            out.append(reads[2 * i])
+        elif kind == 1:
+            out.append(reads[2 * i] + reads[2 * i + 1])
+        elif kind == 2:
+            st, gap = rs.randint(0, L - 12000), rs.randint(600, 4000)
+            s = ref[c0 + st:c0 + st + 2500].tobytes().decode() + ref[c0 + st + 2500 + gap:c0 + st + 5000 + gap].tobytes().decode()
+            out.append(s.translate(comp)[::-1] if rs.randint(2) else s)
+        else:
+            st = rs.randint(0, L - 12000)
+            ins = "".join(rs.choice(list("ACGT"), rs.randint(600, 3000)))
+            out.append(ref[c0 + st:c0 + st + 2000].tobytes().decode() + ins + ref[c0 + st + 2000:c0 + st + 4500].tobytes().decode())
+    bs = [s.encode() for s in out]
+    offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(b) for b in bs])
+    return np.frombuffer(b"".join(bs), dtype=np.uint8).copy(), offs

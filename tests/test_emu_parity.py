@@ -99,3 +99,21 @@ def test_multi_chunk_equals_single_chunk(emu_lib, oracle_mod):
 def test_device_logf_source_matches_host_libm(emu_lib):
     """The glibc-logf restatement in regs.cu (tables typed into the product source) vs the host libm."""
     assert parity.logf_mismatches(emu_lib, 100000) == 0
+
+
+def test_repeats_chimeras_and_rechain(emu_lib, oracle_mod):
+    """Planted repeats + chimeric / SV reads: secondaries, several chains per read and the RMQ
+    long-join re-chain (krmq AVL replay) must all agree with the oracle."""
+    ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
+    c = parity.Case(emu_lib, names, seqs)
+    try:
+        buf, offs = data_gen.make_sv_reads(51, ref, coff, 250)
+        dev, stage_diffs = parity.compare_stages(c, buf, offs, max_reads=250)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert ora.stats["n_rechain"] > 100 and dev.stats["n_rechain"] == ora.stats["n_rechain"]
+        assert stage_diffs == []
+        assert parity.compare_stats(dev, ora) == []
+        assert parity.compare_hits(dev, ora) == []
+        assert (ora.hits["is_primary"] == 0).sum() > 0
+    finally:
+        c.close()

@@ -106,3 +106,18 @@ def test_multi_chunk_equals_oracle(gpu_lib, oracle_mod):
 def test_device_logf_matches_host_libm(gpu_lib):
     """mapq uses logf(); the device restatement of glibc's algorithm is compared with the host libm."""
     assert parity.logf_mismatches(gpu_lib, 300000) == 0
+
+
+def test_repeats_chimeras_and_rechain(gpu_lib, oracle_mod):
+    ref, coff, names, seqs = parity.random_reference(41, [3000000, 1500000], n_repeats=600, rep_min=300, rep_max=6000, rep_div=0.03)
+    c = parity.Case(gpu_lib, names, seqs)
+    try:
+        buf, offs = data_gen.make_sv_reads(51, ref, coff, 6000, 400, 8000)
+        dev, stage_diffs = parity.compare_stages(c, buf, offs, max_reads=300)
+        ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+        assert ora.stats["n_rechain"] > 1000 and dev.stats["n_rechain"] == ora.stats["n_rechain"]
+        assert stage_diffs == []
+        assert parity.compare_stats(dev, ora) == []
+        assert parity.compare_hits(dev, ora) == []
+    finally:
+        c.close()
