@@ -83,3 +83,30 @@ def test_map_one_mapping_only(oracle_mod):
     assert len(r.hits) == 1
     h = r.hits[0]
     assert (h["rid"], h["rs"], h["re"], h["qs"], h["qe"], h["cnt"], h["score"], h["mapq"], h["rev"]) == (1, 1, 394, 1, 394, 75, 393, 60, 0)
+
+
+def test_map_one_reference_assertions(oracle_mod):
+    """`map_one` (src/lib.rs:1094-1106, tests/python_test.py:124-137): exactly one mapping, 0..400.
+    mappy-rs always aligns (flag |= 4, src/lib.rs:339), so this pins that extension reaches both ends."""
+    o = oracle_mod.Oracle(MMI)
+    assert o.get_opt("flag") & 4
+    r = o.map(ENTEROCOCCUS, cs=True)
+    assert len(r.hits) == 1
+    h = r.hits[0]
+    assert (h["rs"], h["re"]) == (0, 400)
+    # SURVEY.md appendix E prediction for the remaining fields
+    assert (h["qs"], h["qe"], h["rev"], h["mapq"], h["mlen"], h["blen"], h["nm"], h["dp_max"], h["is_primary"]) == (0, 400, 0, 60, 400, 400, 0, 800, 1)
+    assert [(int(c) >> 4, int(c) & 15) for c in r.hit_cigar(h)] == [(400, 0)]
+    assert r.cs == b":400"
+
+
+def test_all_fixture_contigs_and_reverse_complements(oracle_mod):
+    """tests/python_test.py:167-178 maps the four contigs 10x each and expects one result per read."""
+    o = oracle_mod.Oracle(MMI)
+    comp = str.maketrans("ACGT", "TGCA")
+    for name, seq in read_fasta(FA):
+        for s, rev in ((seq, 0), (seq.translate(comp)[::-1], 1)):
+            r = o.map(s)
+            assert len(r.hits) == 1
+            h = r.hits[0]
+            assert (o.seq_names[h["rid"]], h["rs"], h["re"], h["rev"], h["mapq"]) == (name, 0, 400, rev, 60)
