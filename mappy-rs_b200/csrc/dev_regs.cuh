@@ -324,6 +324,27 @@ static __device__ void dev_est_err(const DevIndex &di, int qlen, int n_regs, Dev
 	}
 }
 
+/* hit.c: mm_set_inv_mapq -- an inversion takes the smaller mapq of its two neighbours on the target */
+static __device__ void dev_set_inv_mapq(int n_regs, DevReg *regs, uint64_t *zx, uint64_t *zy, int *bkt, int *stk)
+{
+	int i, n_aux;
+	if (n_regs < 3) return;
+	for (i = 0; i < n_regs; ++i) if (REG_INV(regs[i])) break;
+	if (i == n_regs) return;
+	for (i = n_aux = 0; i < n_regs; ++i)
+		if (regs[i].parent == i || regs[i].parent < 0)
+			zy[n_aux] = (uint64_t)i, zx[n_aux++] = (uint64_t)(uint32_t)regs[i].rid << 32 | (uint32_t)regs[i].rs;
+	dev_radix_sort_128x(zx, zy, n_aux, bkt, stk);
+	for (i = 1; i < n_aux - 1; ++i) {
+		DevReg *inv = &regs[(int)zy[i]];
+		if (REG_INV(*inv)) {
+			const DevReg *l = &regs[(int)zy[i - 1]], *r = &regs[(int)zy[i + 1]];
+			uint32_t mq = REG_MAPQ(*l) < REG_MAPQ(*r) ? REG_MAPQ(*l) : REG_MAPQ(*r);
+			REG_SET(*inv, 0, 8, mq);
+		}
+	}
+}
+
 /* hit.c: mm_set_mapq (is_sr = 0).  Inversion regions only arise after alignment. */
 static __device__ void dev_set_mapq(int n_regs, DevReg *regs, int min_chain_sc, int match_sc, int rep_len)
 {

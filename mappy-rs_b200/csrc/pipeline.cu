@@ -16,6 +16,7 @@
 #include "mmg_internal.h"
 #include "dev_common.cuh"
 #include "stages.h"
+#include "extend.h"
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { mmg_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return MMG_ECUDA; } } while (0)
 
@@ -35,6 +36,9 @@ struct mmg_aligner {
 	bool arenas_ready;
 	ChunkDev cd;                       /* arena pointers */
 	unsigned char *rmq_nodes;          /* AVL node arena of the re-chain stage */
+	ExtBufs xb;                        /* extension stage arenas (allocated when MM_F_CIGAR is set) */
+	uint64_t *cg_read_off;
+	uint64_t cap_tb, cap_cg, cap_jobs, big_per_warp;
 	int profile;
 	double stage_ms[MMG_N_STAGES];
 	uint64_t stage_launches[MMG_N_STAGES];
@@ -51,6 +55,7 @@ struct mmg_batch {
 	mmg_hit_t *d_hits; uint64_t hits_cap, n_hits_dev;
 	uint32_t *d_nregs;                 /* per read */
 	unsigned long long *d_stats;
+	uint32_t *d_cigar; uint64_t cigar_cap, n_cigar_dev;
 	std::vector<uint64_t> off;         /* host copy of offsets */
 	std::vector<uint64_t> hit_off;
 	std::vector<mmg_hit_t> hits;
@@ -134,9 +139,25 @@ static int alloc_arenas(mmg_aligner *al)
 	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
 	AL(c.work, 64); AL(c.flags, R);
 	AL(al->rmq_nodes, (2 * A + 2 * R + 2) * RMQ_NODE_BYTES);
+	if (al->mo.flag & MMG_F_CIGAR) {
+		ExtBufs &x = al->xb;
+		x.cap_jobs = al->cap_jobs, x.cap_tb = al->cap_tb, x.cap_cg = al->cap_cg, x.big_per_warp = al->big_per_warp;
+		AL(x.jobs, x.cap_jobs); AL(x.n_jobs, 4); AL(x.xregs, G); AL(x.regs_tmp, G); AL(x.n_sq, R);
+		AL(x.tb, x.cap_tb + 64); AL(x.jcigar, x.cap_cg); AL(x.rcigar, x.cap_cg);
+		AL(x.tb_base, 2); AL(x.cg_base, 2); AL(x.n_pending, 4); AL(x.reg_cap, R);
+		AL(x.big, (uint64_t)al->n_sms * 32 * x.big_per_warp); /* one slice per resident warp of the prep (8x4 per SM) and DP (4x4 per SM) grids */
+		AL(al->cg_read_off, R + 1);
+		x.xr_off = c.r_off;
+	}
 #undef AL
 	al->arenas_ready = true;
 	return MMG_OK;
+}
+
+__global__ void reg_cap_kernel(const uint32_t *n_u, uint32_t *cap, uint32_t n)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) cap[i] = n_u[i] ? 2 * n_u[i] + 4 : 0;
 }
 
 extern "C" {
@@ -169,6 +190,9 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	al->arenas_ready = false;
 	al->profile = 0;
 	al->cap_bases = (uint64_t)96 << 20, al->cap_reads = 1u << 17, al->cap_anchors = (uint64_t)48 << 20, al->cap_regs = (uint64_t)4 << 20;
+	al->cap_tb = (uint64_t)32 << 30, al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48, al->big_per_warp = (uint64_t)1 << 20;
+	memset(&al->xb, 0, sizeof(al->xb));
+	al->cg_read_off = 0;
 	memset(al->stage_ms, 0, sizeof(al->stage_ms));
 	memset(al->stage_launches, 0, sizeof(al->stage_launches));
 	memset(&al->cd, 0, sizeof(al->cd));
@@ -199,6 +223,10 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 	else if (strcmp(key, "chunk_reads") == 0) al->cap_reads = (uint32_t)v;
 	else if (strcmp(key, "anchor_cap") == 0) al->cap_anchors = (uint64_t)v;
 	else if (strcmp(key, "regs_cap") == 0) al->cap_regs = (uint64_t)v;
+	else if (strcmp(key, "tb_cap") == 0) al->cap_tb = (uint64_t)v;
+	else if (strcmp(key, "cigar_cap") == 0) al->cap_cg = (uint64_t)v;
+	else if (strcmp(key, "jobs_cap") == 0) al->cap_jobs = (uint64_t)v;
+	else if (strcmp(key, "big_per_warp") == 0) al->big_per_warp = (uint64_t)v;
 	else { mmg_set_error("unknown key '%s'", key); return MMG_EINVAL; }
 	return MMG_OK;
 }
@@ -211,7 +239,7 @@ int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets
 	b->n_reads = n_reads, b->h_bases = bases, b->h_off = offsets;
 	b->n_bases = n_reads ? offsets[n_reads] - offsets[0] : 0;
 	b->off.assign(offsets, offsets + n_reads + 1);
-	b->d_bases = 0, b->d_off = 0, b->d_hits = 0, b->d_nregs = 0, b->d_stats = 0;
+	b->d_bases = 0, b->d_off = 0, b->d_hits = 0, b->d_nregs = 0, b->d_stats = 0, b->d_cigar = 0, b->cigar_cap = 0, b->n_cigar_dev = 0;
 	b->uploaded = b->ran = b->fetched = false;
 	memset(b->stats, 0, sizeof(b->stats));
 	for (uint32_t i = 0; i < n_reads; ++i) {
@@ -226,6 +254,10 @@ int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets
 	}
 	b->hits_cap = (uint64_t)n_reads * 6 + 1024;
 	if (cudaMalloc((void**)&b->d_hits, b->hits_cap * sizeof(mmg_hit_t)) != cudaSuccess) { mmg_set_error("cudaMalloc failed for the result pool"); mmg_batch_destroy(b); return MMG_ENOMEM; }
+	if (al->mo.flag & MMG_F_CIGAR) {
+		b->cigar_cap = b->n_bases / 2 + ((uint64_t)1 << 16) + (uint64_t)n_reads * 8;
+		if (cudaMalloc((void**)&b->d_cigar, b->cigar_cap * 4) != cudaSuccess) { mmg_set_error("cudaMalloc failed for the CIGAR pool"); mmg_batch_destroy(b); return MMG_ENOMEM; }
+	}
 	if (al->profile) cudaEventRecord(al->ev0, al->stream);
 	/* offsets are rebased so that the device buffer starts at 0 */
 	std::vector<uint64_t> rel(n_reads + 1);
@@ -245,6 +277,80 @@ int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets
 #define STAGE_BEGIN() do { if (al->profile) cudaEventRecord(al->ev0, st); } while (0)
 #define STAGE_END(id) do { al->stage_launches[id] += 1; if (al->profile) { float ms_ = 0; cudaEventRecord(al->ev1, st); cudaEventSynchronize(al->ev1); cudaEventElapsedTime(&ms_, al->ev0, al->ev1); al->stage_ms[id] += ms_; } } while (0)
 
+/* Base-level alignment of the regions of reads [s0, s1): rounds of prep -> DP jobs -> stitch until no
+ * region is left pending (a z-drop split creates a region that is aligned in the next round). */
+static int run_extension(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t s0, uint32_t s1, uint32_t *work, int *wi_, uint64_t *n_cg_sub)
+{
+	cudaStream_t st = al->stream;
+	ExtBufs &xb = al->xb;
+	int wi = *wi_;
+	uint32_t n_jobs_prev = 0;
+	unsigned long long bases[2] = {0, 0}, cg_end = 0;
+	CK(cudaMemsetAsync(xb.n_jobs, 0, 4, st));
+	for (int round = 0; round < 64; ++round) {
+		if (wi + 6 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
+		STAGE_BEGIN();
+		launch_ext_prep(c, al->di, al->dopt, xb, s0, s1, round, al->n_sms, st, work + wi++);
+		uint32_t n_jobs = 0;
+		CK(cudaMemcpyAsync(&n_jobs, xb.n_jobs, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		if (n_jobs > xb.cap_jobs) { mmg_set_error("extension job arena overflow (%u jobs)", n_jobs); return MMG_ENOMEM; }
+		bases[0] = 0, bases[1] = 0;
+		CK(cudaMemcpyAsync(xb.tb_base, bases, 8, cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(xb.cg_base, &cg_end, 8, cudaMemcpyHostToDevice, st));
+		launch_ext_job_scan(xb, n_jobs_prev, n_jobs, st);
+		unsigned long long tb_end = 0;
+		CK(cudaMemcpyAsync(&tb_end, xb.tb_base + 1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&cg_end, xb.cg_base + 1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		STAGE_END(ST_EXTEND);
+		if (cg_end > xb.cap_cg) { mmg_set_error("extension CIGAR arena overflow (%llu > cigar_cap)", cg_end); return MMG_ENOMEM; }
+		/* traceback arena: jobs run in waves that fit cap_tb */
+		std::vector<uint64_t> tboff;
+		if (tb_end > xb.cap_tb) {
+			std::vector<ExtJob> hj(n_jobs - n_jobs_prev);
+			CK(cudaMemcpy(hj.data(), xb.jobs + n_jobs_prev, hj.size() * sizeof(ExtJob), cudaMemcpyDeviceToHost));
+			for (size_t i = 0; i < hj.size(); ++i) {
+				if (hj[i].tb_size > xb.cap_tb) { mmg_set_error("one alignment needs a %llu-byte traceback (> tb_cap)", (unsigned long long)hj[i].tb_size); return MMG_ENOMEM; }
+				tboff.push_back(hj[i].tb_off);
+			}
+		}
+		for (uint32_t j0 = n_jobs_prev; j0 < n_jobs;) {
+			uint32_t j1 = n_jobs;
+			uint64_t wave_base = 0;
+			if (!tboff.empty()) {
+				wave_base = tboff[j0 - n_jobs_prev];
+				j1 = j0;
+				while (j1 < n_jobs && (j1 + 1 < n_jobs ? tboff[j1 + 1 - n_jobs_prev] : tb_end) - wave_base <= xb.cap_tb) ++j1;
+			}
+			ExtBufs xw = xb;
+			xw.tb = xb.tb - wave_base;
+			if (wi + 4 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
+			STAGE_BEGIN();
+			launch_ext_dp(c, al->di, al->dopt, xw, j0, j1, ext_dp_grid(al->n_sms), st, work + wi++);
+			STAGE_END(ST_EXTEND);
+			j0 = j1;
+		}
+		STAGE_BEGIN();
+		CK(cudaMemsetAsync(xb.n_pending, 0, 4, st));
+		launch_ext_stitch(c, al->di, al->dopt, xb, s0, s1, round, al->n_sms, st, work + wi++);
+		uint32_t n_pending = 0;
+		CK(cudaMemcpyAsync(&n_pending, xb.n_pending, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		STAGE_END(ST_EXTEND);
+		n_jobs_prev = n_jobs;
+		if (n_pending == 0) break;
+	}
+	STAGE_BEGIN();
+	launch_ext_final(c, al->di, al->dopt, xb, s0, s1, al->n_sms, st, work + wi++);
+	launch_scan_u32(xb.n_sq + s0, al->cg_read_off + s0, s1 - s0, st);
+	CK(cudaMemcpyAsync(n_cg_sub, al->cg_read_off + s1, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	STAGE_END(ST_EXTEND);
+	*wi_ = wi;
+	return MMG_OK;
+}
+
 int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 {
 	if (!b->uploaded) { mmg_set_error("batch not uploaded"); return MMG_EINVAL; }
@@ -254,7 +360,7 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 	cudaStream_t st = al->stream;
 	memset(al->stage_ms, 0, sizeof(al->stage_ms));
 	memset(al->stage_launches, 0, sizeof(al->stage_launches));
-	b->n_hits_dev = 0;
+	b->n_hits_dev = 0, b->n_cigar_dev = 0;
 	CK(cudaMemsetAsync(b->d_stats, 0, MMG_N_STATS * 8, st));
 	CK(cudaEventRecord(al->ev_run0, st));
 	const uint32_t n = b->n_reads;
@@ -290,10 +396,19 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 			STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
 			STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
 			STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);
+			const bool with_cigar = (al->mo.flag & MMG_F_CIGAR) != 0;
 			STAGE_BEGIN();
-			launch_scan_u32(c.n_u + s0, c.r_off + s0, s1 - s0, st);
+			if (with_cigar) { /* region slices leave room for the pieces z-drop splits insert */
+				MMG_LAUNCH(reg_cap_kernel, (int)((s1 - s0 + 255) / 256), 256, 0, st, (const uint32_t*)(c.n_u + s0), al->xb.reg_cap + s0, s1 - s0);
+				launch_scan_u32(al->xb.reg_cap + s0, c.r_off + s0, s1 - s0, st);
+			} else launch_scan_u32(c.n_u + s0, c.r_off + s0, s1 - s0, st);
 			STAGE_END(ST_SCAN);
 			STAGE_BEGIN(); launch_regs(c, al->di, al->dopt, s0, s1, al->cap_regs, al->n_sms, st, work + wi++); STAGE_END(ST_REGS);
+			uint64_t n_cg_sub = 0;
+			if (with_cigar) {
+				int rc2 = run_extension(al, b, c, s0, s1, work, &wi, &n_cg_sub);
+				if (rc2) return rc2;
+			}
 			STAGE_BEGIN();
 			launch_scan_u32(c.n_regs + s0, c.h_off + s0, s1 - s0, st);
 			STAGE_END(ST_SCAN);
@@ -305,6 +420,11 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 			if (b->n_hits_dev + n_hits_sub > b->hits_cap) { mmg_set_error("result pool overflow (%llu hits)", (unsigned long long)(b->n_hits_dev + n_hits_sub)); return MMG_ENOMEM; }
 			STAGE_BEGIN();
 			launch_pack_hits(c, s0, s1, b->d_hits + b->n_hits_dev, al->n_sms, st);
+			if (with_cigar) {
+				if (b->n_cigar_dev + n_cg_sub > b->cigar_cap) { mmg_set_error("CIGAR pool overflow (%llu ops)", (unsigned long long)(b->n_cigar_dev + n_cg_sub)); return MMG_ENOMEM; }
+				launch_pack_cigar(c, al->xb, s0, s1, b->d_hits + b->n_hits_dev, b->d_cigar + b->n_cigar_dev, b->n_cigar_dev, al->cg_read_off, al->n_sms, st);
+				b->n_cigar_dev += n_cg_sub;
+			}
 			CK(cudaMemcpyAsync(b->d_nregs + r0 + s0, c.n_regs + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToDevice, st));
 			STAGE_END(ST_REGS);
 			b->n_hits_dev += n_hits_sub;
@@ -331,6 +451,8 @@ int mmg_batch_fetch(mmg_aligner *al, mmg_batch *b)
 	STAGE_BEGIN();
 	if (b->n_reads) CK(cudaMemcpyAsync(nregs.data(), b->d_nregs, (size_t)b->n_reads * 4, cudaMemcpyDeviceToHost, st));
 	if (b->n_hits_dev) CK(cudaMemcpyAsync(b->hits.data(), b->d_hits, b->n_hits_dev * sizeof(mmg_hit_t), cudaMemcpyDeviceToHost, st));
+	b->cigar.resize(b->n_cigar_dev);
+	if (b->n_cigar_dev) CK(cudaMemcpyAsync(b->cigar.data(), b->d_cigar, b->n_cigar_dev * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(b->stats, b->d_stats, MMG_N_STATS * 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	STAGE_END(ST_D2H);
@@ -359,6 +481,7 @@ void mmg_batch_destroy(mmg_batch *b)
 	if (b->d_hits) cudaFree(b->d_hits);
 	if (b->d_nregs) cudaFree(b->d_nregs);
 	if (b->d_stats) cudaFree(b->d_stats);
+	if (b->d_cigar) cudaFree(b->d_cigar);
 	delete b;
 }
 

@@ -106,7 +106,7 @@ def make_sv_reads(seed, ref, coff, n_reads, len_min=400, len_max=4000):
     out = []
     n_ctg = len(coff) - 1
     for i in range(n_reads):
-        kind = rs.randint(4)
+        kind = rs.randint(6)
         c = rs.randint(n_ctg)
         c0, L = int(coff[c]), int(coff[c + 1] - coff[c])
         if kind == 0 or L < 14000:
@@ -117,10 +117,20 @@ def make_sv_reads(seed, ref, coff, n_reads, len_min=400, len_max=4000):
             st, gap = rs.randint(0, L - 12000), rs.randint(600, 4000)
             s = ref[c0 + st:c0 + st + 2500].tobytes().decode() + ref[c0 + st + 2500 + gap:c0 + st + 5000 + gap].tobytes().decode()
             out.append(s.translate(comp)[::-1] if rs.randint(2) else s)
-        else:
+        elif kind == 3:
             st = rs.randint(0, L - 12000)
             ins = "".join(rs.choice(list("ACGT"), rs.randint(600, 3000)))
             out.append(ref[c0 + st:c0 + st + 2000].tobytes().decode() + ins + ref[c0 + st + 2000:c0 + st + 4500].tobytes().decode())
+        elif kind == 4:  # inversion: the middle stretch is reverse-complemented (z-drop split + inversion alignment)
+            st, il = rs.randint(0, L - 12000), rs.randint(200, 1500)
+            mid = ref[c0 + st + 2000:c0 + st + 2000 + il].tobytes().decode().translate(comp)[::-1]
+            s = ref[c0 + st:c0 + st + 2000].tobytes().decode() + mid + ref[c0 + st + 2000 + il:c0 + st + 4500 + il].tobytes().decode()
+            out.append(s.translate(comp)[::-1] if rs.randint(2) else s)
+        else:  # a stretch replaced by unrelated sequence of the same length (z-drop without a gap)
+            st, il = rs.randint(0, L - 12000), rs.randint(300, 1500)
+            mid = "".join(rs.choice(list("ACGT"), il))
+            s = ref[c0 + st:c0 + st + 2000].tobytes().decode() + mid + ref[c0 + st + 2000 + il:c0 + st + 4500 + il].tobytes().decode()
+            out.append(s.translate(comp)[::-1] if rs.randint(2) else s)
     bs = [s.encode() for s in out]
     offs = np.zeros(len(bs) + 1, dtype=np.uint64)
     offs[1:] = np.cumsum([len(b) for b in bs])

@@ -117,3 +117,56 @@ def test_repeats_chimeras_and_rechain(emu_lib, oracle_mod):
         assert (ora.hits["is_primary"] == 0).sum() > 0
     finally:
         c.close()
+
+
+def _small_arenas(c):
+    for k, v in (("tb_cap", 1 << 28), ("cigar_cap", 1 << 24), ("jobs_cap", 1 << 16), ("chunk_bases", 1 << 22),
+                 ("anchor_cap", 1 << 20), ("chunk_reads", 4096), ("regs_cap", 1 << 16), ("big_per_warp", 1 << 18)):
+        c.aligner.set(k, v)
+
+
+def test_cigar_mode_plain_reads(emu_lib, oracle_mod):
+    """mappy-rs' real mode (MM_F_CIGAR forced, src/lib.rs:339): extension + gap filling + CIGAR, bit-exact."""
+    ref, coff, names, seqs = parity.random_reference(61, [200000])
+    c = parity.Case(emu_lib, names, seqs, cigar=True)
+    try:
+        _small_arenas(c)
+        buf, offs, _ = data_gen.make_reads(71, ref, coff, 80, 300, 3000)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_hits(dev, ora) == []
+        assert len(dev.cigar) == len(ora.cigar) > 1000
+    finally:
+        c.close()
+
+
+def test_cigar_mode_splits_and_inversions(emu_lib, oracle_mod):
+    """z-drop splits (mm_split_reg), inversion alignments (mm_align1_inv + ksw_ll_i16), inv mapq, secondaries."""
+    ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
+    c = parity.Case(emu_lib, names, seqs, cigar=True)
+    try:
+        _small_arenas(c)
+        buf, offs = data_gen.make_sv_reads(51, ref, coff, 90)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_hits(dev, ora) == []
+        f = ora.hits["flags"]
+        assert ((f & 8) > 0).sum() > 5 and ((f & 2) > 0).sum() > 2   # splits and inversions really occur
+    finally:
+        c.close()
+
+
+def test_cigar_mode_fixture_map_one(emu_lib, oracle_mod):
+    """`map_one` through the product's kernel source: 1 hit, 0..400, 400M (src/lib.rs:1094-1106)."""
+    c = parity.Case(emu_lib, None, None, mmi=MMI, cigar=True)
+    try:
+        _small_arenas(c)
+        seqs = [c.oracle.seq(n) for n in c.oracle.seq_names]
+        buf, offs = oracle_mod.pack_reads(seqs)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 1)
+        assert parity.compare_hits(dev, ora) == []
+        assert [(int(h["rs"]), int(h["re"]), int(h["mapq"])) for h in dev.hits] == [(0, 400, 60)] * 4
+        assert all([(int(x) >> 4, int(x) & 15) for x in dev.hit_cigar(h)] == [(400, 0)] for h in dev.hits)
+    finally:
+        c.close()

@@ -121,3 +121,55 @@ def test_repeats_chimeras_and_rechain(gpu_lib, oracle_mod):
         assert parity.compare_hits(dev, ora) == []
     finally:
         c.close()
+
+
+def test_cigar_mode_config1_sample(case5mb, gpu_lib, oracle_mod):
+    """CIGAR on (what mappy-rs always runs): 3000 config-1 reads, every field and every CIGAR op."""
+    c = parity.Case(gpu_lib, ["chr1"], [case5mb.ref.tobytes()], cigar=True)
+    try:
+        buf, offs, _ = data_gen.config1_reads(case5mb.ref, case5mb.coff, 3000)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+        assert parity.compare_hits(dev, ora) == []
+        assert len(dev.cigar) == len(ora.cigar)
+    finally:
+        c.close()
+
+
+def test_cigar_mode_splits_and_inversions(gpu_lib, oracle_mod):
+    ref, coff, names, seqs = parity.random_reference(41, [3000000, 1500000], n_repeats=600, rep_min=300, rep_max=6000, rep_div=0.03)
+    c = parity.Case(gpu_lib, names, seqs, cigar=True)
+    try:
+        buf, offs = data_gen.make_sv_reads(51, ref, coff, 1500, 400, 6000)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+        assert parity.compare_hits(dev, ora) == []
+        f = ora.hits["flags"]
+        assert ((f & 8) > 0).sum() > 50 and ((f & 2) > 0).sum() > 20
+    finally:
+        c.close()
+
+
+def test_cigar_mode_hifi(gpu_lib, oracle_mod):
+    ref, coff, names, seqs = parity.random_reference(21, [2000000])
+    c = parity.Case(gpu_lib, names, seqs, preset="map-hifi", cigar=True)
+    try:
+        buf, offs, _ = data_gen.make_reads(22, ref, coff, 300, 10000, 25000, len_mean=15000, len_sd=2000, p_sub=0.002, p_ins=0.0015, p_del=0.0015)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+        assert parity.compare_hits(dev, ora) == []
+    finally:
+        c.close()
+
+
+def test_cigar_mode_fixture_map_one(gpu_lib, oracle_mod):
+    c = parity.Case(gpu_lib, None, None, mmi=MMI, cigar=True)
+    try:
+        seqs = [c.oracle.seq(n) for n in c.oracle.seq_names] * 10
+        buf, offs = oracle_mod.pack_reads(seqs)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 1)
+        assert parity.compare_hits(dev, ora) == []
+        assert [(int(h["rs"]), int(h["re"])) for h in dev.hits] == [(0, 400)] * 40
+    finally:
+        c.close()
