@@ -179,11 +179,16 @@ const uint64_t *mmg_batch_hit_off(const mmg_batch *b);
 const mmg_hit_t *mmg_batch_hits(const mmg_batch *b);
 uint64_t mmg_batch_n_cigar(const mmg_batch *b);
 const uint32_t *mmg_batch_cigar(const mmg_batch *b);
-/* replaces mm_gen_cs(.., no_iden=1) / mm_gen_MD called by crate minimap2 when
+/* replaces mm_gen_cs(.., no_iden) / mm_gen_MD called by crate minimap2 when
  * cs/MD are requested (src/lib.rs:484-485, 589-590): writes a NUL-terminated
- * string for hit `hit_idx`, returns its length or a negative code */
-int mmg_batch_gen_cs(const mmg_aligner *al, const mmg_batch *b, uint64_t hit_idx, char *buf, size_t cap);
-int mmg_batch_gen_md(const mmg_aligner *al, const mmg_batch *b, uint64_t hit_idx, char *buf, size_t cap);
+ * string for one hit given its CIGAR and the read; returns the length (call
+ * with buf = NULL to size) or a negative code */
+int mmg_gen_cs(const mmg_index *idx, const mmg_hit_t *hit, const uint32_t *cigar, const char *seq, int qlen, int no_iden, char *buf, size_t cap);
+int mmg_gen_md(const mmg_index *idx, const mmg_hit_t *hit, const uint32_t *cigar, const char *seq, int qlen, char *buf, size_t cap);
+/* the same for every hit of a batch at once (which: 0 = short cs, 1 = MD); strings are concatenated,
+ * str_off has n_hits+1 entries; returns the total length, writes only if it fits cap */
+int64_t mmg_gen_tags(const mmg_index *idx, const char *bases, const uint64_t *offsets, uint32_t n_reads, const uint64_t *hit_off,
+                     const mmg_hit_t *hits, const uint32_t *cigar_pool, int which, int n_threads, char *buf, uint64_t cap, uint64_t *str_off);
 /* replaces freeing reg.p and the mm_reg1_t array (crate minimap2 Aligner::map) */
 void mmg_batch_destroy(mmg_batch *b);
 

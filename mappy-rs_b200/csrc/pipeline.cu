@@ -536,9 +536,6 @@ int64_t mmg_debug_dump(mmg_aligner *al, mmg_batch *b, int which, uint64_t *x, ui
 	return (int64_t)tot;
 }
 
-int mmg_batch_gen_cs(const mmg_aligner *, const mmg_batch *, uint64_t, char *, size_t) { mmg_set_error("cs needs CIGAR (not built yet)"); return MMG_EUNSUP; }
-int mmg_batch_gen_md(const mmg_aligner *, const mmg_batch *, uint64_t, char *, size_t) { mmg_set_error("MD needs CIGAR (not built yet)"); return MMG_EUNSUP; }
-
 const char *mmg_version(void)
 {
 #ifdef MMG_EMU

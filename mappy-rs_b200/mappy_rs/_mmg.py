@@ -58,8 +58,8 @@ EXPORTS = ["mmg_set_opt", "mmg_mapopt_update", "mmg_index_open", "mmg_index_buil
            "mmg_index_info", "mmg_index_seq_name", "mmg_index_seq_len", "mmg_index_name2id", "mmg_index_getseq",
            "mmg_index_entries", "mmg_aligner_create", "mmg_aligner_destroy", "mmg_aligner_set", "mmg_map_batch",
            "mmg_batch_upload", "mmg_batch_run", "mmg_batch_fetch", "mmg_batch_n_reads", "mmg_batch_n_hits",
-           "mmg_batch_hit_off", "mmg_batch_hits", "mmg_batch_n_cigar", "mmg_batch_cigar", "mmg_batch_gen_cs",
-           "mmg_batch_gen_md", "mmg_batch_destroy", "mmg_batch_stats", "mmg_stage_times", "mmg_stage_name",
+           "mmg_batch_hit_off", "mmg_batch_hits", "mmg_batch_n_cigar", "mmg_batch_cigar", "mmg_gen_cs",
+           "mmg_gen_md", "mmg_gen_tags", "mmg_debug_logf", "mmg_batch_destroy", "mmg_batch_stats", "mmg_stage_times", "mmg_stage_name",
            "mmg_last_run_ms", "mmg_debug_dump", "mmg_last_error", "mmg_version", "mmg_sizeof_hit"]
 
 
@@ -102,8 +102,10 @@ class Lib:
             getattr(L, nm).restype = c_u64; getattr(L, nm).argtypes = [c_vp]
         for nm in ("mmg_batch_hit_off", "mmg_batch_hits", "mmg_batch_cigar"):
             getattr(L, nm).restype = c_vp; getattr(L, nm).argtypes = [c_vp]
-        L.mmg_batch_gen_cs.argtypes = [c_vp, c_vp, c_u64, c_vp, ctypes.c_size_t]
-        L.mmg_batch_gen_md.argtypes = [c_vp, c_vp, c_u64, c_vp, ctypes.c_size_t]
+        L.mmg_gen_cs.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, ctypes.c_size_t]
+        L.mmg_gen_md.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, ctypes.c_size_t]
+        L.mmg_gen_tags.restype = c_i64
+        L.mmg_gen_tags.argtypes = [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_u64, c_vp]
         L.mmg_batch_destroy.argtypes = [c_vp]
         L.mmg_batch_stats.argtypes = [c_vp, c_vp]
         L.mmg_stage_times.argtypes = [c_vp, c_vp, c_vp]
@@ -248,3 +250,21 @@ class DeviceAligner:
         n = self.lib.L.mmg_debug_dump(self.h, b, which, x.ctypes.data, y.ctypes.data, cap, off.ctypes.data)
         self.lib.check(int(n))
         return x[:n], y[:n], off
+
+
+def gen_tags(lib, index, buf, offs, res, which, n_threads=4):
+    """cs (which=0) or MD (which=1) strings of every hit of a Batch: list[bytes|None]."""
+    n_reads, n_hits = len(offs) - 1, len(res.hits)
+    if n_hits == 0:
+        return []
+    buf = np.ascontiguousarray(buf, dtype=np.uint8); offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    hit_off = np.ascontiguousarray(res.hit_off, dtype=np.uint64)
+    hits = np.ascontiguousarray(res.hits); cig = np.ascontiguousarray(res.cigar, dtype=np.uint32)
+    so = np.zeros(n_hits + 1, dtype=np.uint64)
+    args = [index.h, buf.ctypes.data, offs.ctypes.data, n_reads, hit_off.ctypes.data, hits.ctypes.data, cig.ctypes.data if len(cig) else None, which, n_threads]
+    tot = lib.check(int(lib.L.mmg_gen_tags(*args, None, 0, so.ctypes.data)))
+    out = np.zeros(max(tot, 1), dtype=np.uint8)
+    lib.check(int(lib.L.mmg_gen_tags(*args, out.ctypes.data, tot, so.ctypes.data)))
+    raw = out.tobytes()
+    has = (res.hits["flags"] & 32) != 0
+    return [raw[int(so[i]):int(so[i + 1])] if has[i] else None for i in range(n_hits)]

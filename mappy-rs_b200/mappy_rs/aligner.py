@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference's Python module `mappy_rs` (src/lib.rs), above the C ABI.
+
+The reference is a Rust/PyO3 extension; no Rust toolchain exists in this image,
+so the operator interface is mirrored here with the same names, argument
+meaning, defaults and error behaviour, and every data-path call goes through
+libmmg.so (include/mmg.h).  Citations are to /root/reference/src/lib.rs.
+
+  Aligner(...)               lib.rs:311-436   constructor / option plumbing
+  Aligner.map                lib.rs:472-514   one read, blocking
+  Aligner.enable_threading   lib.rs:541-636   (worker pool -> device batch pipeline)
+  Aligner.map_batch          lib.rs:640-648, 771-906  streaming iterator of (mappings, dict)
+  Aligner.seq / seq_names / k / w / n_seq / __bool__   lib.rs:439-470, 651-670
+  Mapping                    lib.rs:106-285
+There is no CPU mapping path: without libmmg.so or a CUDA device construction fails.
+"""
+import collections
+import ctypes
+import threading
+import time
+
+import numpy as np
+
+from . import _mmg
+
+_WORK_QUEUE_CAP = 50000   # lib.rs:429-430
+_CIGAR_OPS = "MIDNSHP=X"
+
+
+class Mapping:
+    """Result of an alignment (lib.rs:106-154).  `cigar` is a list of (length, op) tuples."""
+    __slots__ = ("query_start", "query_end", "_strand", "target_name", "target_len", "target_start", "target_end",
+                 "match_len", "block_len", "mapq", "is_primary", "cigar", "NM", "MD", "cs")
+
+    def __init__(self, query_start, query_end, strand, target_name, target_len, target_start, target_end,
+                 match_len, block_len, mapq, is_primary, cigar, NM, MD, cs):
+        self.query_start, self.query_end, self._strand = query_start, query_end, strand
+        self.target_name, self.target_len, self.target_start, self.target_end = target_name, target_len, target_start, target_end
+        self.match_len, self.block_len, self.mapq, self.is_primary = match_len, block_len, mapq, is_primary
+        self.cigar, self.NM, self.MD, self.cs = cigar, NM, MD, cs
+
+    # mappy-style aliases (lib.rs:196-284)
+    ctg = property(lambda s: s.target_name)
+    ctg_len = property(lambda s: s.target_len)
+    r_st = property(lambda s: s.target_start)
+    r_en = property(lambda s: s.target_end)
+    q_st = property(lambda s: s.query_start)
+    q_en = property(lambda s: s.query_end)
+    strand = property(lambda s: s._strand)          # +1 / -1 (lib.rs:231-237)
+    blen = property(lambda s: s.block_len)
+    mlen = property(lambda s: s.match_len)
+
+    @property
+    def cigar_str(self):
+        out = []
+        for n, op in self.cigar:
+            if not 0 <= op <= 8:
+                raise ValueError("Invalid CIGAR code `{op}`")   # lib.rs:269
+            out.append("%d%s" % (n, _CIGAR_OPS[op]))
+        return "".join(out)
+
+    def __str__(self):   # lib.rs:159-179: PAF without query name / length
+        return "\t".join(str(x) for x in (self.query_start, self.query_end, "+" if self._strand > 0 else "-", self.target_name,
+                                            self.target_len, self.target_start, self.target_end, self.match_len, self.block_len,
+                                            self.mapq, "tp:A:P" if self.is_primary else "tp:A:S", "cg:Z:" + self.cigar_str))
+
+    def __repr__(self):  # lib.rs:186-188 ({self:#?})
+        f = [("query_start", self.query_start), ("query_end", self.query_end), ("strand", "Forward" if self._strand > 0 else "Reverse"),
+             ("target_name", '"%s"' % self.target_name), ("target_len", self.target_len), ("target_start", self.target_start),
+             ("target_end", self.target_end), ("match_len", self.match_len), ("block_len", self.block_len), ("mapq", self.mapq),
+             ("is_primary", "true" if self.is_primary else "false"), ("cigar", self.cigar), ("NM", self.NM),
+             ("MD", "None" if self.MD is None else 'Some("%s")' % self.MD), ("cs", "None" if self.cs is None else 'Some("%s")' % self.cs)]
+        return "Mapping {\n" + "".join("    %s: %s,\n" % kv for kv in f) + "}"
+
+    def __eq__(self, o):
+        return isinstance(o, Mapping) and all(getattr(self, k) == getattr(o, k) for k in self.__slots__)
+
+
+def _mappings_from(res, names, lens, cs_list, md_list, lo, hi):
+    """hits[lo:hi] of a Batch -> list[Mapping] (field mapping of crate minimap2 Aligner::map, lib.rs:493-509)."""
+    out = []
+    hits, cig = res.hits, res.cigar
+    for i in range(lo, hi):
+        h = hits[i]
+        c0, nc = int(h["cigar_off"]), int(h["n_cigar"])
+        ops = cig[c0:c0 + nc]
+        rid = int(h["rid"])
+        out.append(Mapping(int(h["qs"]), int(h["qe"]), -1 if h["rev"] else 1, names[rid], lens[rid], int(h["rs"]), int(h["re"]),
+                           int(h["mlen"]), int(h["blen"]), int(h["mapq"]), bool(h["is_primary"]),
+                           [(int(x) >> 4, int(x) & 0xf) for x in ops], int(h["nm"]),
+                           md_list[i].decode() if md_list is not None and md_list[i] is not None else None,
+                           cs_list[i].decode() if cs_list is not None and cs_list[i] is not None else None))
+    return out
+
+
+class AlignmentBatchResultIter:
+    """Iterator returned by map_batch (lib.rs:923-992): yields (list[Mapping], dict) in completion order."""
+
+    def __init__(self):
+        self._q = collections.deque()
+        self._cv = threading.Condition()
+        self._finished = False
+        self._error = None
+
+    def _put(self, items):
+        with self._cv:
+            self._q.extend(items)
+            self._cv.notify_all()
+
+    def _finish(self, error=None):
+        with self._cv:
+            self._finished, self._error = True, error
+            self._cv.notify_all()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        with self._cv:
+            while not self._q and not self._finished:
+                self._cv.wait(0.05)
+            if self._q:
+                return self._q.popleft()
+            if self._error is not None:
+                err, self._error = self._error, None
+                raise RuntimeError("device mapping failed: %s" % err)
+            raise StopIteration("Finished")   # lib.rs:976
+
+
+class Aligner:
+    """Aligner mimicking mappy / mappy-rs (lib.rs:288-671) on the B200 mapping library."""
+
+    def __init__(self, fn_idx_in=None, preset=None, k=None, w=None, min_cnt=None, min_chain_score=None, min_dp_score=None,
+                 bw=None, best_n=None, n_threads=3, fn_idx_out=None, max_frag_len=None, extra_flags=None, seq=None, scoring=None,
+                 device=0, _lib=None, _tune=None):
+        lib = self._lib = _lib or _mmg.Lib()
+        io, mo = _mmg.IdxOpt(), _mmg.MapOpt()
+        lib.check(lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mo)))                     # lib.rs:333
+        if preset is not None:
+            lib.check(lib.L.mmg_set_opt(str(preset).encode(), ctypes.byref(io), ctypes.byref(mo)))  # lib.rs:336
+        mo.flag |= 4                                                                                # lib.rs:339
+        io.batch_size |= 0x7fffffffffffffff                                                         # lib.rs:340
+        if k is not None: io.k = k
+        if w is not None: io.w = w
+        if min_cnt is not None: mo.min_cnt = min_cnt
+        if min_chain_score is not None: mo.min_chain_score = min_chain_score
+        if min_dp_score is not None: mo.min_dp_max = min_dp_score
+        if bw is not None: mo.bw = bw
+        if best_n is not None: mo.best_n = best_n
+        if max_frag_len is not None: mo.max_frag_len = max_frag_len
+        if extra_flags is not None: mo.flag |= extra_flags
+        if scoring is not None and len(scoring) >= 4:                                               # lib.rs:369-385
+            mo.a, mo.b, mo.q, mo.e = (int(x) for x in scoring[:4])
+            mo.q2, mo.e2 = mo.q, mo.e
+            if len(scoring) >= 6:
+                mo.q2, mo.e2 = int(scoring[4]), int(scoring[5])
+                if len(scoring) >= 7:
+                    mo.sc_ambi = int(scoring[6])
+        if seq is not None:
+            raise NotImplementedError("Not Implemented")                                            # lib.rs:388-390
+        if fn_idx_out is not None:
+            raise NotImplementedError("Not Implemented")                                            # lib.rs:391-394
+        self._index = self._aligner = None
+        self.n_threads = 0                                                                          # lib.rs:426
+        if fn_idx_in is None:
+            raise RuntimeError("Did not create or open an index")                                   # lib.rs:435
+        self._index = _mmg.Index.open(lib, str(fn_idx_in), io, n_threads)                           # lib.rs:398-412
+        lib.check(lib.L.mmg_mapopt_update(ctypes.byref(mo), self._index.h))                         # lib.rs:414
+        self._io, self._mo = io, mo
+        self._names = [self._index.seq_name(i) for i in range(self._index.n_seq)]
+        self._lens = [self._index.seq_len(i) for i in range(self._index.n_seq)]
+        self._aligner = _mmg.DeviceAligner(lib, self._index, mo, device=device)   # uploads the index once; raises without a GPU
+        for key, val in (_tune or {}).items():   # device arena sizes (not mapping semantics)
+            self._aligner.set(key, val)
+        self._lock = threading.Lock()
+
+    # ---- index accessors ------------------------------------------------------------
+    def __bool__(self):
+        return self._index is not None                                                              # lib.rs:651-653
+
+    @property
+    def seq_names(self):
+        if self._index is None:
+            raise RuntimeError("Index hasn't loaded")                                               # lib.rs:441-443
+        return list(self._names)
+
+    @property
+    def k(self): return self._index.k
+    @property
+    def w(self): return self._index.w
+    @property
+    def n_seq(self): return self._index.n_seq
+
+    def seq(self, name, start=0, end=2147483647):
+        """(Sub)sequence of a contig, or None (lib.rs:464-470, 706-766)."""
+        if self._index is None or ((self._mo.flag & 4) and (self._index.flag & 2)):
+            return None
+        rid = self._index.name2id(name)
+        if rid < 0 or rid >= self._index.n_seq:
+            return None
+        ln = self._lens[rid]
+        if start >= ln or start >= end:
+            return None
+        if end < 0 or end > ln:
+            end = ln
+        codes = self._index.getseq(rid, start, end)
+        if codes is None or (codes > 4).any():
+            return None
+        return np.frombuffer(b"ACGTN", dtype=np.uint8)[codes].tobytes().decode()
+
+    # ---- mapping ----------------------------------------------------------------------
+    def _map_reads(self, seqs, cs, md):
+        """list[str] -> per-read lists of Mapping, through mmg_map_batch (host buffers in, results out)."""
+        bs = [s.encode() for s in seqs]
+        offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(b) for b in bs])
+        buf = np.frombuffer(b"".join(bs), dtype=np.uint8) if offs[-1] else np.zeros(1, dtype=np.uint8)
+        with self._lock:
+            res = self._aligner.map_batch(buf, offs)
+        cs_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 0) if cs else None
+        md_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 1) if md else None
+        ho = res.hit_off
+        return [_mappings_from(res, self._names, self._lens, cs_l, md_l, int(ho[i]), int(ho[i + 1])) for i in range(len(bs))]
+
+    def map(self, seq, seq2=None, cs=False, MD=False):
+        """Map a single read, blocking (lib.rs:472-514)."""
+        if seq2 is not None:
+            raise NotImplementedError("Using `seq2` is not implemented")
+        if self._index is None:
+            raise RuntimeError("No index")
+        if len(seq) == 0:
+            raise RuntimeError("Sequence is empty")   # crate minimap2 Aligner::map
+        return self._map_reads([seq], cs, MD)[0]
+
+    def map_no_op(self, _seq, seq2=None, _cs=False, _MD=False):
+        """Canned mapping used to isolate wrapper overhead (lib.rs:517-533, 675-693)."""
+        if seq2 is not None:
+            raise NotImplementedError("Using `seq2` is not implemented")
+        return [Mapping(0, 1000, 1, "Hello", 101010, 10, 1010, 1000, 1000, 60, True, [], 0, None, "Cigar string")]
+
+    def enable_threading(self, n_threads):
+        """lib.rs:541-636 spawns CPU workers; here it arms the device batch pipeline (the GPU replaces the pool)."""
+        self.n_threads = int(n_threads)
+
+    def map_batch(self, seqs, back_off=True):
+        """Align a batch of dicts with a `seq` key; returns an iterator of (list[Mapping], dict) (lib.rs:640-648, 771-906)."""
+        if self.n_threads == 0:
+            raise RuntimeError("Multi threading not enabled on this instance. Please call `.enable_threading()`")
+        if isinstance(seqs, (dict, set, frozenset)) or not (isinstance(seqs, (list, tuple)) or hasattr(seqs, "__next__") or
+                                                            (hasattr(seqs, "__getitem__") and hasattr(seqs, "__len__"))):
+            raise TypeError("Unsupported batch type, pass a list, iter, generator or tuple")
+        res_iter = AlignmentBatchResultIter()
+        work = collections.deque()          # the bounded work queue of lib.rs:301,429
+        cv = threading.Condition()
+        state = {"done": False, "abort": False}
+
+        def worker():
+            try:
+                while True:
+                    with cv:
+                        # drain when the producer is done or the queue is full (large device batches; and the
+                        # documented 50000-entry limit of the work queue stays observable)
+                        while not state["done"] and len(work) < _WORK_QUEUE_CAP:
+                            cv.wait(0.01)
+                        items = list(work)
+                        work.clear()
+                        done = state["done"]
+                        cv.notify_all()
+                        if state["abort"]:   # the producer raised: nothing is returned to the caller (lib.rs:847-866 return early)
+                            break
+                    if items:
+                        per_read = self._map_reads([s for _, s in items], True, False)   # cs=true, md=false: lib.rs:587-593
+                        res_iter._put([(m, d) for m, (d, _) in zip(per_read, items)])
+                    if done and not items:
+                        break
+                res_iter._finish()
+            except Exception as e:   # surfaced to the consumer instead of silently dropping reads (lib.rs:621-623 logs and drops)
+                res_iter._finish(error=str(e))
+
+        th = threading.Thread(target=worker, daemon=True)
+        th.start()
+        self._workers = [t for t in getattr(self, "_workers", []) if t.is_alive()] + [th]
+        ok = False
+        try:
+            for id_num, item in enumerate(iter(seqs)):
+                if not isinstance(item, dict) or not all(isinstance(k_, str) for k_ in item):
+                    raise TypeError("Element in iterable is not a dictionary")
+                data = dict(item)                      # lib.rs:847-855: a new dict with the same keys / values
+                if "seq" not in item:
+                    raise KeyError("AHHH Key 🗝️  not found in iterated dictionary")
+                seq = item["seq"]
+                if not isinstance(seq, str):
+                    raise ValueError("`seq` must be a string")
+                with cv:
+                    if len(work) >= _WORK_QUEUE_CAP:
+                        if not back_off:
+                            raise RuntimeError(
+                                "Internal error adding data to work queue, without backoff. Work(({id_num}, ..)) {id_num}. "
+                                "Is your fastq batch larger than 50000? Perhaps try `map_batch` with back_off=True?".format(id_num=id_num))
+                        cv.notify_all()
+                        deadline = time.time() + 3.15   # 50 ms doubling, 6 attempts (lib.rs:871-885)
+                        while len(work) >= _WORK_QUEUE_CAP and time.time() < deadline:
+                            cv.wait(0.05)
+                    work.append((data, seq))
+            ok = True
+        finally:
+            with cv:
+                state["done"] = True
+                state["abort"] = not ok
+                cv.notify_all()
+        return res_iter
+
+    def close(self):
+        for t in getattr(self, "_workers", []):   # device buffers must outlive in-flight batches
+            t.join()
+        self._workers = []
+        if self._aligner is not None:
+            self._aligner.close()
+            self._aligner = None
+        if self._index is not None:
+            self._index.close()
+            self._index = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
