@@ -95,7 +95,7 @@ def run_reference(args, rank, world):
     n_sample = min(args.reads, args.cpu_sample)
     ref, coff, names, buf, offs = workload(n_sample, 0)
     o = mo.Oracle(names=names, seqs=[ref.tobytes()])
-    o.set_opt("flag", 0)
+    o.set_opt("flag", 4 if args.cigar else 0)
     cores = os.cpu_count() or 1
     for _ in range(args.warmup):
         o.map_batch(buf[:int(offs[2000])], offs[:2001], cores)
@@ -129,7 +129,7 @@ def run_ours(args, rank, local_rank, world):
     n_reads, n_bases = len(offs) - 1, int(offs[-1])
     io, mopt = _mmg.IdxOpt(), _mmg.MapOpt()
     lib.check(lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mopt)))
-    mopt.flag = 0  # mapping-only (configs[1])
+    mopt.flag = 4 if args.cigar else 0  # configs[1] is mapping-only
     idx = _mmg.Index.build(lib, io, names, [ref.tobytes()])
     lib.check(lib.L.mmg_mapopt_update(ctypes.byref(mopt), idx.h))
     al = _mmg.DeviceAligner(lib, idx, mopt, device=local_rank)
@@ -182,7 +182,7 @@ def run_ours(args, rank, local_rank, world):
     d2h = 0
     for _ in range(args.steps):
         r = al.map_batch(hptr, offs)
-        d2h = r.hits.nbytes + n_reads * 4 + 80
+        d2h = r.hits.nbytes + r.cigar.nbytes + n_reads * 4 + 80
     barrier()
     e2e_s = maxrank((time.perf_counter() - t0) / args.steps)
     sampler.stop_flag = True
@@ -201,7 +201,7 @@ def run_ours(args, rank, local_rank, world):
         "metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "mbases_per_s": world * n_bases / (ms_per_step / 1e3) / 1e6,
-        "config": {"workload": "BASELINE.json configs[1]: 5 Mb synthetic reference (seed 1), %d simulated 1-10 kb ONT reads (3%% sub, 2%% ins, 3%% del; seed 2), map-ont, mapping-only" % n_reads,
+        "config": {"workload": "BASELINE.json configs[1]: 5 Mb synthetic reference (seed 1), %d simulated 1-10 kb ONT reads (3%% sub, 2%% ins, 3%% del; seed 2), map-ont, %s" % (n_reads, "CIGAR on" if args.cigar else "mapping-only"),
                    "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "l2": "inputs (%.0f MB) larger than L2" % (n_bases / 1e6), "parallelism": "reads sharded, index replicated"},
         "e2e": {"value": world * n_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": n_bases + (n_reads + 1) * 8, "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
@@ -215,7 +215,7 @@ def run_ours(args, rank, local_rank, world):
         import mm2oracle as mo
         ns = min(n_reads, args.cpu_sample)
         o = mo.Oracle(names=names, seqs=[ref.tobytes()])
-        o.set_opt("flag", 0)
+        o.set_opt("flag", 4 if args.cigar else 0)
         cores = os.cpu_count() or 1
         t0 = time.perf_counter()
         ores = o.map_batch(buf[:int(offs[ns])], offs[:ns + 1], cores)
@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--reads", type=int, default=200000)
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cigar", action="store_true", help="MM_F_CIGAR on (what mappy-rs itself always runs); default is configs[1] mapping-only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
