@@ -125,13 +125,21 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 				int brk = -1;
 				if (M == 0) { n_skip -= __popc(I); if (n_skip < 0) n_skip = 0; }
 				else {
-					uint32_t bits = I | M;
-					while (bits) {
-						int b = __ffs((int)bits) - 1;
-						bits &= bits - 1;
-						if (I >> b & 1u) { if (n_skip > 0) --n_skip; }
-						else if (++n_skip > max_skip) { brk = b; break; }
+					/* every lane is a map x -> max(x + sa, sc): improving = (-1, 0), marked = (+1, -inf),
+					 * otherwise the identity; maps of this form are closed under composition, so an
+					 * inclusive warp scan gives n_skip after every lane */
+					const bool mk = marked && !improve;
+					int32_t sa = improve ? -1 : mk ? 1 : 0, sc2 = improve ? 0 : -(1 << 28);
+#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						int32_t pa = __shfl_up_sync(MMG_FULL, sa, d), pc = __shfl_up_sync(MMG_FULL, sc2, d);
+						if (lane >= d) { pc += sa; sc2 = pc > sc2 ? pc : sc2; sa += pa; }
 					}
+					int32_t after = n_skip + sa;
+					if (after < sc2) after = sc2;
+					const uint32_t over = __ballot_sync(MMG_FULL, mk && after > max_skip);
+					if (over) brk = __ffs((int)over) - 1;
+					else n_skip = __shfl_sync(MMG_FULL, after, 31);
 				}
 				const int limit = brk >= 0 ? brk : 32;
 				const int32_t c2 = lane < limit ? sc : INT32_MIN_;

@@ -44,6 +44,26 @@ struct mmg_aligner {
 	uint64_t stage_launches[MMG_N_STAGES];
 	cudaEvent_t ev0, ev1, ev_run0, ev_run1;
 	double last_run_ms;
+	/* per-stage timing without host synchronisation: event pairs are recorded on the compute stream
+	 * and read back when the run has finished */
+	std::vector<cudaEvent_t> ev_pool;
+	std::vector<int> ev_stage;
+	size_t ev_used;
+	/* streamed mode (mmg_map_batch): chunk k+1 is copied in on s_in while chunk k is computed on
+	 * `stream`, and the results of finished sub-ranges are copied out on s_out */
+	cudaStream_t s_in, s_out;
+	bool stream_ready;
+	char *in_bases[2]; uint64_t *in_off[2]; uint64_t *h_in_off[2];
+	cudaEvent_t ev_in[2], ev_free[2];
+	struct ResSlot {
+		mmg_hit_t *d_hits, *h_hits; uint64_t hits_cap;
+		uint32_t *d_cigar, *h_cigar; uint64_t cigar_cap;
+		uint32_t *d_nregs, *h_nregs; uint64_t nregs_cap;
+		cudaEvent_t ev_packed, ev_out;
+		bool pending; uint64_t n_hits, n_cigar, hit_base, cigar_base; uint32_t read0, n_reads;
+	} rs[2];
+	unsigned long long *d_stats_pool;
+	uint64_t n_sub;                    /* sub-ranges issued by the current streamed call */
 };
 
 struct mmg_batch {
@@ -62,6 +82,7 @@ struct mmg_batch {
 	std::vector<uint32_t> cigar;
 	uint64_t stats[MMG_N_STATS];
 	bool uploaded, ran, fetched;
+	bool streamed;                     /* inputs/results go through the aligner's streaming slots */
 	/* debug: arenas of the LAST chunk stay valid until the next run */
 	uint32_t dbg_r0, dbg_r1;
 };
@@ -137,7 +158,7 @@ static int alloc_arenas(mmg_aligner *al)
 	AL(c.cx, A); AL(c.cy, A); AL(c.u, A);
 	AL(c.n_u, R); AL(c.n_v, R); AL(c.r_off, R + 1);
 	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
-	AL(c.work, 64); AL(c.flags, R);
+	AL(c.work, 64); AL(c.flags, R); AL(c.big_list, R);
 	AL(al->rmq_nodes, (2 * A + 2 * R + 2) * RMQ_NODE_BYTES);
 	if (al->mo.flag & MMG_F_CIGAR) {
 		ExtBufs &x = al->xb;
@@ -187,6 +208,9 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	CK(cudaEventCreate(&al->ev_run0));
 	CK(cudaEventCreate(&al->ev_run1));
 	al->last_run_ms = 0;
+	al->ev_used = 0, al->s_in = 0, al->s_out = 0, al->stream_ready = false, al->d_stats_pool = 0, al->n_sub = 0;
+	memset(al->in_bases, 0, sizeof(al->in_bases)), memset(al->in_off, 0, sizeof(al->in_off)), memset(al->h_in_off, 0, sizeof(al->h_in_off));
+	memset(al->ev_in, 0, sizeof(al->ev_in)), memset(al->ev_free, 0, sizeof(al->ev_free)), memset(al->rs, 0, sizeof(al->rs));
 	al->arenas_ready = false;
 	al->profile = 0;
 	al->cap_bases = (uint64_t)96 << 20, al->cap_reads = 1u << 17, al->cap_anchors = (uint64_t)48 << 20, al->cap_regs = (uint64_t)4 << 20;
@@ -208,6 +232,23 @@ void mmg_aligner_destroy(mmg_aligner *al)
 	if (!al) return;
 	for (size_t i = 0; i < al->dev_allocs.size(); ++i) cudaFree(al->dev_allocs[i]);
 	if (al->stream) cudaStreamDestroy(al->stream);
+	if (al->s_in) cudaStreamDestroy(al->s_in);
+	if (al->s_out) cudaStreamDestroy(al->s_out);
+	for (int k = 0; k < 2; ++k) {
+		if (al->h_in_off[k]) cudaFreeHost(al->h_in_off[k]);
+		if (al->ev_in[k]) cudaEventDestroy(al->ev_in[k]);
+		if (al->ev_free[k]) cudaEventDestroy(al->ev_free[k]);
+		mmg_aligner::ResSlot &r = al->rs[k];
+		if (r.ev_packed) cudaEventDestroy(r.ev_packed);
+		if (r.ev_out) cudaEventDestroy(r.ev_out);
+		if (r.d_hits) cudaFree(r.d_hits);
+		if (r.d_cigar) cudaFree(r.d_cigar);
+		if (r.d_nregs) cudaFree(r.d_nregs);
+		if (r.h_hits) cudaFreeHost(r.h_hits);
+		if (r.h_cigar) cudaFreeHost(r.h_cigar);
+		if (r.h_nregs) cudaFreeHost(r.h_nregs);
+	}
+	for (size_t i = 0; i < al->ev_pool.size(); ++i) cudaEventDestroy(al->ev_pool[i]);
 	if (al->ev0) cudaEventDestroy(al->ev0);
 	if (al->ev1) cudaEventDestroy(al->ev1);
 	if (al->ev_run0) cudaEventDestroy(al->ev_run0);
@@ -241,6 +282,7 @@ int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets
 	b->off.assign(offsets, offsets + n_reads + 1);
 	b->d_bases = 0, b->d_off = 0, b->d_hits = 0, b->d_nregs = 0, b->d_stats = 0, b->d_cigar = 0, b->cigar_cap = 0, b->n_cigar_dev = 0;
 	b->uploaded = b->ran = b->fetched = false;
+	b->streamed = false;
 	memset(b->stats, 0, sizeof(b->stats));
 	for (uint32_t i = 0; i < n_reads; ++i) {
 		uint64_t l = offsets[i + 1] - offsets[i];
@@ -274,8 +316,27 @@ int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets
 	return MMG_OK;
 }
 
-#define STAGE_BEGIN() do { if (al->profile) cudaEventRecord(al->ev0, st); } while (0)
-#define STAGE_END(id) do { al->stage_launches[id] += 1; if (al->profile) { float ms_ = 0; cudaEventRecord(al->ev1, st); cudaEventSynchronize(al->ev1); cudaEventElapsedTime(&ms_, al->ev0, al->ev1); al->stage_ms[id] += ms_; } } while (0)
+static cudaEvent_t stage_event(mmg_aligner *al, int stage)
+{
+	if (al->ev_used == al->ev_pool.size()) {
+		cudaEvent_t e = 0;
+		cudaEventCreate(&e);
+		al->ev_pool.push_back(e), al->ev_stage.push_back(stage);
+	}
+	al->ev_stage[al->ev_used] = stage;
+	return al->ev_pool[al->ev_used++];
+}
+/* called after the compute stream has been synchronised */
+static void stage_collect(mmg_aligner *al)
+{
+	for (size_t i = 0; i + 1 < al->ev_used; i += 2) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, al->ev_pool[i], al->ev_pool[i + 1]) == cudaSuccess) al->stage_ms[al->ev_stage[i + 1]] += ms;
+	}
+	al->ev_used = 0;
+}
+#define STAGE_BEGIN() do { if (al->profile) cudaEventRecord(stage_event(al, -1), st); } while (0)
+#define STAGE_END(id) do { al->stage_launches[id] += 1; if (al->profile) cudaEventRecord(stage_event(al, id), st); } while (0)
 
 /* Base-level alignment of the regions of reads [s0, s1): rounds of prep -> DP jobs -> stitch until no
  * region is left pending (a z-drop split creates a region that is aligned in the next round). */
@@ -351,6 +412,179 @@ static int run_extension(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t s0
 	return MMG_OK;
 }
 
+} // extern "C"
+
+/* ---- streamed mode plumbing ------------------------------------------------------------------ */
+
+static int stream_setup(mmg_aligner *al)
+{
+	if (al->stream_ready) return MMG_OK;
+	CK(cudaStreamCreateWithFlags(&al->s_in, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&al->s_out, cudaStreamNonBlocking));
+	for (int k = 0; k < 2; ++k) {
+		int rc;
+		if ((rc = dev_alloc(al, &al->in_bases[k], al->cap_bases + 64))) return rc;
+		if ((rc = dev_alloc(al, &al->in_off[k], (uint64_t)al->cap_reads + 1))) return rc;
+		CK(cudaMallocHost((void**)&al->h_in_off[k], ((size_t)al->cap_reads + 1) * 8));
+		CK(cudaEventCreateWithFlags(&al->ev_in[k], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&al->ev_free[k], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&al->rs[k].ev_packed, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&al->rs[k].ev_out, cudaEventDisableTiming));
+	}
+	if (cudaMalloc((void**)&al->d_stats_pool, MMG_N_STATS * 8) != cudaSuccess) { mmg_set_error("cudaMalloc failed"); return MMG_ENOMEM; }
+	al->dev_allocs.push_back(al->d_stats_pool);
+	al->stream_ready = true;
+	return MMG_OK;
+}
+
+template<typename T> static int slot_grow(T **d, T **h, uint64_t *cap, uint64_t need)
+{
+	if (need <= *cap) return MMG_OK;
+	uint64_t n = *cap ? *cap : 1024;
+	while (n < need) n *= 2;
+	if (*d) cudaFree(*d);
+	if (*h) cudaFreeHost(*h);
+	*d = 0, *h = 0, *cap = 0;
+	if (cudaMalloc((void**)d, n * sizeof(T)) != cudaSuccess || cudaMallocHost((void**)h, n * sizeof(T)) != cudaSuccess) {
+		mmg_set_error("cannot allocate %llu bytes for a result slot", (unsigned long long)(n * sizeof(T)));
+		return MMG_ENOMEM;
+	}
+	*cap = n;
+	return MMG_OK;
+}
+
+/* move the finished results of a slot from pinned staging into the batch */
+static int slot_drain(mmg_aligner *al, mmg_batch *b, int k)
+{
+	mmg_aligner::ResSlot &r = al->rs[k];
+	if (!r.pending) return MMG_OK;
+	CK(cudaEventSynchronize(r.ev_out));
+	if (b->hits.size() < r.hit_base + r.n_hits) b->hits.resize(r.hit_base + r.n_hits);
+	if (r.n_hits) memcpy(b->hits.data() + r.hit_base, r.h_hits, r.n_hits * sizeof(mmg_hit_t));
+	if (b->cigar.size() < r.cigar_base + r.n_cigar) b->cigar.resize(r.cigar_base + r.n_cigar);
+	if (r.n_cigar) memcpy(b->cigar.data() + r.cigar_base, r.h_cigar, r.n_cigar * 4);
+	uint64_t acc = r.hit_base;
+	for (uint32_t i = 0; i < r.n_reads; ++i) b->hit_off[r.read0 + i] = acc, acc += r.h_nregs[i];
+	if (acc != r.hit_base + r.n_hits) { mmg_set_error("internal: hit count mismatch in a result slot (%llu vs %llu)", (unsigned long long)acc, (unsigned long long)(r.hit_base + r.n_hits)); return MMG_ECUDA; }
+	r.pending = false;
+	return MMG_OK;
+}
+
+/* One chunk of reads [r0, r1) of batch b through every stage.  c.seq / c.off / c.off0 are set by the caller
+ * (whole-batch device buffers in resident mode, an input slot in streamed mode). */
+static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, std::vector<uint64_t> &h_aoff)
+{
+	cudaStream_t st = al->stream;
+	uint32_t *work = c.work;
+	int wi = 0;
+	CK(cudaMemsetAsync(c.work, 0, 64 * 4, st));
+	CK(cudaMemsetAsync(c.flags, 0, (size_t)c.n_reads * 4, st));
+	STAGE_BEGIN(); launch_sketch(c, al->di, al->n_sms, st, work + wi++); STAGE_END(ST_SKETCH);
+	STAGE_BEGIN(); launch_seed(c, al->di, al->dopt, al->n_sms, st, work + wi++); STAGE_END(ST_SEED);
+	STAGE_BEGIN(); launch_scan_u32(c.n_a, c.a_off, c.n_reads, st); STAGE_END(ST_SCAN);
+	uint64_t a_total = 0;
+	CK(cudaMemcpyAsync(&a_total, c.a_off + c.n_reads, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const bool split = a_total > al->cap_anchors;
+	if (split) { /* the per-read offsets are only needed to cut sub-ranges */
+		h_aoff.resize(c.n_reads + 1);
+		CK(cudaMemcpyAsync(h_aoff.data(), c.a_off, (size_t)(c.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	/* sub-ranges whose anchors fit the anchor-sized arenas */
+	for (uint32_t s0 = 0; s0 < c.n_reads;) {
+		uint32_t s1 = s0;
+		if (!split) s1 = c.n_reads, c.a_off0 = 0;
+		else {
+			while (s1 < c.n_reads && h_aoff[s1 + 1] - h_aoff[s0] <= al->cap_anchors) ++s1;
+			if (s1 == s0) { mmg_set_error("read %u has %llu anchors, more than anchor_cap", r0 + s0, (unsigned long long)(h_aoff[s0 + 1] - h_aoff[s0])); return MMG_ENOMEM; }
+			c.a_off0 = h_aoff[s0];
+		}
+		if (wi + 10 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
+		STAGE_BEGIN(); launch_expand(c, al->di, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_EXPAND);
+		STAGE_BEGIN(); launch_sort(c, s0, s1, al->n_sms, st, work + wi); wi += 3; STAGE_END(ST_SORT);
+		STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
+		STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
+		STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);
+		const bool with_cigar = (al->mo.flag & MMG_F_CIGAR) != 0;
+		STAGE_BEGIN();
+		if (with_cigar) { /* region slices leave room for the pieces z-drop splits insert */
+			MMG_LAUNCH(reg_cap_kernel, (int)((s1 - s0 + 255) / 256), 256, 0, st, (const uint32_t*)(c.n_u + s0), al->xb.reg_cap + s0, s1 - s0);
+			launch_scan_u32(al->xb.reg_cap + s0, c.r_off + s0, s1 - s0, st);
+		} else launch_scan_u32(c.n_u + s0, c.r_off + s0, s1 - s0, st);
+		STAGE_END(ST_SCAN);
+		STAGE_BEGIN(); launch_regs(c, al->di, al->dopt, s0, s1, al->cap_regs, al->n_sms, st, work + wi++); STAGE_END(ST_REGS);
+		uint64_t n_cg_sub = 0;
+		if (with_cigar) {
+			int rc2 = run_extension(al, b, c, s0, s1, work, &wi, &n_cg_sub);
+			if (rc2) return rc2;
+		}
+		STAGE_BEGIN();
+		launch_scan_u32(c.n_regs + s0, c.h_off + s0, s1 - s0, st);
+		STAGE_END(ST_SCAN);
+		uint64_t n_hits_sub = 0, n_regs_sub = 0;
+		CK(cudaMemcpyAsync(&n_hits_sub, c.h_off + s1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(&n_regs_sub, c.r_off + s1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		if (n_regs_sub > al->cap_regs) { mmg_set_error("region arena overflow (%llu > regs_cap)", (unsigned long long)n_regs_sub); return MMG_ENOMEM; }
+		if (!b->streamed) {
+			if (b->n_hits_dev + n_hits_sub > b->hits_cap) { mmg_set_error("result pool overflow (%llu hits)", (unsigned long long)(b->n_hits_dev + n_hits_sub)); return MMG_ENOMEM; }
+			STAGE_BEGIN();
+			launch_pack_hits(c, s0, s1, b->d_hits + b->n_hits_dev, al->n_sms, st);
+			if (with_cigar) {
+				if (b->n_cigar_dev + n_cg_sub > b->cigar_cap) { mmg_set_error("CIGAR pool overflow (%llu ops)", (unsigned long long)(b->n_cigar_dev + n_cg_sub)); return MMG_ENOMEM; }
+				launch_pack_cigar(c, al->xb, s0, s1, b->d_hits + b->n_hits_dev, b->d_cigar + b->n_cigar_dev, b->n_cigar_dev, al->cg_read_off, al->n_sms, st);
+			}
+			CK(cudaMemcpyAsync(b->d_nregs + r0 + s0, c.n_regs + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToDevice, st));
+			STAGE_END(ST_REGS);
+		} else {
+			/* results of this sub-range leave through a slot: pack on the compute stream, copy out on s_out */
+			const int k = (int)(al->n_sub++ & 1);
+			mmg_aligner::ResSlot &r = al->rs[k];
+			int rc;
+			if ((rc = slot_drain(al, b, k))) return rc;
+			if ((rc = slot_grow(&r.d_hits, &r.h_hits, &r.hits_cap, n_hits_sub + 1))) return rc;
+			if ((rc = slot_grow(&r.d_nregs, &r.h_nregs, &r.nregs_cap, (uint64_t)(s1 - s0) + 1))) return rc;
+			if (with_cigar && (rc = slot_grow(&r.d_cigar, &r.h_cigar, &r.cigar_cap, n_cg_sub + 1))) return rc;
+			STAGE_BEGIN();
+			launch_pack_hits(c, s0, s1, r.d_hits, al->n_sms, st);
+			if (with_cigar) launch_pack_cigar(c, al->xb, s0, s1, r.d_hits, r.d_cigar, b->n_cigar_dev, al->cg_read_off, al->n_sms, st);
+			CK(cudaMemcpyAsync(r.d_nregs, c.n_regs + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToDevice, st));
+			STAGE_END(ST_REGS);
+			CK(cudaEventRecord(r.ev_packed, st));
+			CK(cudaStreamWaitEvent(al->s_out, r.ev_packed, 0));
+			if (n_hits_sub) CK(cudaMemcpyAsync(r.h_hits, r.d_hits, n_hits_sub * sizeof(mmg_hit_t), cudaMemcpyDeviceToHost, al->s_out));
+			if (n_cg_sub) CK(cudaMemcpyAsync(r.h_cigar, r.d_cigar, n_cg_sub * 4, cudaMemcpyDeviceToHost, al->s_out));
+			CK(cudaMemcpyAsync(r.h_nregs, r.d_nregs, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToHost, al->s_out));
+			CK(cudaEventRecord(r.ev_out, al->s_out));
+			/* the next sub-range that packs into this slot must not start before the copy-out is done */
+			CK(cudaStreamWaitEvent(st, r.ev_out, 0));
+			r.pending = true, r.n_hits = n_hits_sub, r.n_cigar = n_cg_sub, r.hit_base = b->n_hits_dev, r.cigar_base = b->n_cigar_dev;
+			r.read0 = r0 + s0, r.n_reads = s1 - s0;
+		}
+		b->n_cigar_dev += n_cg_sub;
+		b->n_hits_dev += n_hits_sub;
+		b->dbg_r0 = r0 + s0, b->dbg_r1 = r0 + s1;
+		s0 = s1;
+	}
+	return MMG_OK;
+}
+
+static void cut_chunks(const mmg_aligner *al, const mmg_batch *b, std::vector<uint32_t> &cuts)
+{
+	const uint32_t n = b->n_reads;
+	cuts.clear();
+	cuts.push_back(0);
+	for (uint32_t r0 = 0; r0 < n;) {
+		uint32_t r1 = r0;
+		while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= al->cap_bases) ++r1;
+		cuts.push_back(r1);
+		r0 = r1;
+	}
+}
+
+extern "C" {
+
 int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 {
 	if (!b->uploaded) { mmg_set_error("batch not uploaded"); return MMG_EINVAL; }
@@ -360,83 +594,26 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 	cudaStream_t st = al->stream;
 	memset(al->stage_ms, 0, sizeof(al->stage_ms));
 	memset(al->stage_launches, 0, sizeof(al->stage_launches));
+	al->ev_used = 0;
 	b->n_hits_dev = 0, b->n_cigar_dev = 0;
 	CK(cudaMemsetAsync(b->d_stats, 0, MMG_N_STATS * 8, st));
 	CK(cudaEventRecord(al->ev_run0, st));
-	const uint32_t n = b->n_reads;
 	std::vector<uint64_t> h_aoff;
-	for (uint32_t r0 = 0; r0 < n;) {
-		/* chunk = as many reads as fit the base-sized arenas */
-		uint32_t r1 = r0;
-		while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= al->cap_bases) ++r1;
-		if (r1 == r0) { mmg_set_error("read %u does not fit the chunk arenas", r0); return MMG_EINVAL; }
+	std::vector<uint32_t> cuts;
+	cut_chunks(al, b, cuts);
+	for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+		const uint32_t r0 = cuts[k], r1 = cuts[k + 1];
 		ChunkDev c = al->cd;
 		c.n_reads = r1 - r0;
 		c.seq = b->d_bases, c.off = b->d_off + r0, c.off0 = b->off[r0];
 		c.stats = b->d_stats;
-		uint32_t *work = c.work;
-		int wi = 0;
-		CK(cudaMemsetAsync(c.work, 0, 64 * 4, st));
-		CK(cudaMemsetAsync(c.flags, 0, (size_t)c.n_reads * 4, st));
-		STAGE_BEGIN(); launch_sketch(c, al->di, al->n_sms, st, work + wi++); STAGE_END(ST_SKETCH);
-		STAGE_BEGIN(); launch_seed(c, al->di, al->dopt, al->n_sms, st, work + wi++); STAGE_END(ST_SEED);
-		STAGE_BEGIN(); launch_scan_u32(c.n_a, c.a_off, c.n_reads, st); STAGE_END(ST_SCAN);
-		h_aoff.resize(c.n_reads + 1);
-		CK(cudaMemcpyAsync(h_aoff.data(), c.a_off, (size_t)(c.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		/* sub-ranges whose anchors fit the anchor-sized arenas */
-		for (uint32_t s0 = 0; s0 < c.n_reads;) {
-			uint32_t s1 = s0;
-			while (s1 < c.n_reads && h_aoff[s1 + 1] - h_aoff[s0] <= al->cap_anchors) ++s1;
-			if (s1 == s0) { mmg_set_error("read %u has %llu anchors, more than anchor_cap", r0 + s0, (unsigned long long)(h_aoff[s0 + 1] - h_aoff[s0])); return MMG_ENOMEM; }
-			c.a_off0 = h_aoff[s0];
-			if (wi + 8 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
-			STAGE_BEGIN(); launch_expand(c, al->di, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_EXPAND);
-			STAGE_BEGIN(); launch_sort(c, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_SORT);
-			STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
-			STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
-			STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);
-			const bool with_cigar = (al->mo.flag & MMG_F_CIGAR) != 0;
-			STAGE_BEGIN();
-			if (with_cigar) { /* region slices leave room for the pieces z-drop splits insert */
-				MMG_LAUNCH(reg_cap_kernel, (int)((s1 - s0 + 255) / 256), 256, 0, st, (const uint32_t*)(c.n_u + s0), al->xb.reg_cap + s0, s1 - s0);
-				launch_scan_u32(al->xb.reg_cap + s0, c.r_off + s0, s1 - s0, st);
-			} else launch_scan_u32(c.n_u + s0, c.r_off + s0, s1 - s0, st);
-			STAGE_END(ST_SCAN);
-			STAGE_BEGIN(); launch_regs(c, al->di, al->dopt, s0, s1, al->cap_regs, al->n_sms, st, work + wi++); STAGE_END(ST_REGS);
-			uint64_t n_cg_sub = 0;
-			if (with_cigar) {
-				int rc2 = run_extension(al, b, c, s0, s1, work, &wi, &n_cg_sub);
-				if (rc2) return rc2;
-			}
-			STAGE_BEGIN();
-			launch_scan_u32(c.n_regs + s0, c.h_off + s0, s1 - s0, st);
-			STAGE_END(ST_SCAN);
-			uint64_t n_hits_sub = 0, n_regs_sub = 0;
-			CK(cudaMemcpyAsync(&n_hits_sub, c.h_off + s1, 8, cudaMemcpyDeviceToHost, st));
-			CK(cudaMemcpyAsync(&n_regs_sub, c.r_off + s1, 8, cudaMemcpyDeviceToHost, st));
-			CK(cudaStreamSynchronize(st));
-			if (n_regs_sub > al->cap_regs) { mmg_set_error("region arena overflow (%llu > regs_cap)", (unsigned long long)n_regs_sub); return MMG_ENOMEM; }
-			if (b->n_hits_dev + n_hits_sub > b->hits_cap) { mmg_set_error("result pool overflow (%llu hits)", (unsigned long long)(b->n_hits_dev + n_hits_sub)); return MMG_ENOMEM; }
-			STAGE_BEGIN();
-			launch_pack_hits(c, s0, s1, b->d_hits + b->n_hits_dev, al->n_sms, st);
-			if (with_cigar) {
-				if (b->n_cigar_dev + n_cg_sub > b->cigar_cap) { mmg_set_error("CIGAR pool overflow (%llu ops)", (unsigned long long)(b->n_cigar_dev + n_cg_sub)); return MMG_ENOMEM; }
-				launch_pack_cigar(c, al->xb, s0, s1, b->d_hits + b->n_hits_dev, b->d_cigar + b->n_cigar_dev, b->n_cigar_dev, al->cg_read_off, al->n_sms, st);
-				b->n_cigar_dev += n_cg_sub;
-			}
-			CK(cudaMemcpyAsync(b->d_nregs + r0 + s0, c.n_regs + s0, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToDevice, st));
-			STAGE_END(ST_REGS);
-			b->n_hits_dev += n_hits_sub;
-			b->dbg_r0 = r0 + s0, b->dbg_r1 = r0 + s1;
-			s0 = s1;
-		}
-		r0 = r1;
+		if ((rc = run_chunk(al, b, c, r0, h_aoff))) return rc;
 	}
 	CK(cudaEventRecord(al->ev_run1, st));
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
 	{ float ms = 0; cudaEventElapsedTime(&ms, al->ev_run0, al->ev_run1); al->last_run_ms = ms; }
+	stage_collect(al);
 	b->ran = true;
 	return MMG_OK;
 }
@@ -444,18 +621,20 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 int mmg_batch_fetch(mmg_aligner *al, mmg_batch *b)
 {
 	if (!b->ran) { mmg_set_error("batch not run"); return MMG_EINVAL; }
+	if (b->streamed) { b->fetched = true; return MMG_OK; }
 	CK(cudaSetDevice(al->device));
 	cudaStream_t st = al->stream;
 	std::vector<uint32_t> nregs(b->n_reads + 1);
 	b->hits.resize(b->n_hits_dev);
-	STAGE_BEGIN();
+	CK(cudaEventRecord(al->ev0, st));
 	if (b->n_reads) CK(cudaMemcpyAsync(nregs.data(), b->d_nregs, (size_t)b->n_reads * 4, cudaMemcpyDeviceToHost, st));
 	if (b->n_hits_dev) CK(cudaMemcpyAsync(b->hits.data(), b->d_hits, b->n_hits_dev * sizeof(mmg_hit_t), cudaMemcpyDeviceToHost, st));
 	b->cigar.resize(b->n_cigar_dev);
 	if (b->n_cigar_dev) CK(cudaMemcpyAsync(b->cigar.data(), b->d_cigar, b->n_cigar_dev * 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaMemcpyAsync(b->stats, b->d_stats, MMG_N_STATS * 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaEventRecord(al->ev1, st));
 	CK(cudaStreamSynchronize(st));
-	STAGE_END(ST_D2H);
+	{ float ms = 0; cudaEventElapsedTime(&ms, al->ev0, al->ev1); al->stage_ms[ST_D2H] += ms; al->stage_launches[ST_D2H] += 1; }
 	b->hit_off.resize(b->n_reads + 1);
 	uint64_t acc = 0;
 	for (uint32_t i = 0; i < b->n_reads; ++i) b->hit_off[i] = acc, acc += nregs[i];
@@ -465,11 +644,93 @@ int mmg_batch_fetch(mmg_aligner *al, mmg_batch *b)
 	return MMG_OK;
 }
 
+/* Streamed mapping of a host batch: the H2D copy of chunk k+1 (s_in) and the D2H copy of finished
+ * results (s_out) overlap the kernels of chunk k; no per-batch device allocation. */
+static int map_batch_streamed(mmg_aligner *al, mmg_batch *b)
+{
+	int rc;
+	if ((rc = alloc_arenas(al)) || (rc = stream_setup(al))) return rc;
+	cudaStream_t st = al->stream;
+	memset(al->stage_ms, 0, sizeof(al->stage_ms));
+	memset(al->stage_launches, 0, sizeof(al->stage_launches));
+	al->ev_used = 0, al->n_sub = 0;
+	al->rs[0].pending = al->rs[1].pending = false;
+	b->n_hits_dev = 0, b->n_cigar_dev = 0;
+	b->hit_off.assign((size_t)b->n_reads + 1, 0);
+	b->hits.reserve((size_t)b->n_reads + (b->n_reads >> 3) + 16);
+	std::vector<uint32_t> cuts;
+	cut_chunks(al, b, cuts);
+	const size_t n_chunks = cuts.size() - 1;
+	CK(cudaMemsetAsync(al->d_stats_pool, 0, MMG_N_STATS * 8, st));
+	CK(cudaEventRecord(al->ev_run0, st));
+	auto copy_in = [&](size_t k) -> int {
+		const int slot = (int)(k & 1);
+		const uint32_t r0 = cuts[k], r1 = cuts[k + 1];
+		if (k >= 2) CK(cudaEventSynchronize(al->ev_in[slot])); /* the host staging of the offsets is free again */
+		uint64_t *ho = al->h_in_off[slot];
+		const uint64_t base = b->off[r0];
+		for (uint32_t i = r0; i <= r1; ++i) ho[i - r0] = b->off[i] - base;
+		if (k >= 2) CK(cudaStreamWaitEvent(al->s_in, al->ev_free[slot], 0)); /* chunk k-2 has finished reading the slot */
+		CK(cudaMemcpyAsync(al->in_bases[slot], b->h_bases + b->h_off[0] + base, b->off[r1] - base, cudaMemcpyHostToDevice, al->s_in));
+		CK(cudaMemcpyAsync(al->in_off[slot], ho, (size_t)(r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, al->s_in));
+		CK(cudaEventRecord(al->ev_in[slot], al->s_in));
+		return MMG_OK;
+	};
+	std::vector<uint64_t> h_aoff;
+	if (n_chunks && (rc = copy_in(0))) return rc;
+	for (size_t k = 0; k < n_chunks; ++k) {
+		const int slot = (int)(k & 1);
+		if (k + 1 < n_chunks && (rc = copy_in(k + 1))) return rc;
+		CK(cudaStreamWaitEvent(st, al->ev_in[slot], 0));
+		ChunkDev c = al->cd;
+		c.n_reads = cuts[k + 1] - cuts[k];
+		c.seq = al->in_bases[slot], c.off = al->in_off[slot], c.off0 = 0;
+		c.stats = al->d_stats_pool;
+		if ((rc = run_chunk(al, b, c, cuts[k], h_aoff))) return rc;
+		CK(cudaEventRecord(al->ev_free[slot], st));
+	}
+	CK(cudaMemcpyAsync(b->stats, al->d_stats_pool, MMG_N_STATS * 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaEventRecord(al->ev_run1, st));
+	CK(cudaStreamSynchronize(st));
+	/* the slots were filled in issue order: drain the older one first so the vectors grow monotonically */
+	const int older = (int)(al->n_sub & 1);
+	if ((rc = slot_drain(al, b, older)) || (rc = slot_drain(al, b, older ^ 1))) return rc;
+	CK(cudaStreamSynchronize(al->s_out));
+	CK(cudaGetLastError());
+	{ float ms = 0; cudaEventElapsedTime(&ms, al->ev_run0, al->ev_run1); al->last_run_ms = ms; }
+	stage_collect(al);
+	b->hits.resize(b->n_hits_dev), b->cigar.resize(b->n_cigar_dev);
+	b->hit_off[b->n_reads] = b->n_hits_dev;
+	b->ran = b->fetched = true;
+	return MMG_OK;
+}
+
 int mmg_map_batch(mmg_aligner *al, const char *bases, const uint64_t *offsets, uint32_t n_reads, mmg_batch **out)
 {
-	int rc = mmg_batch_upload(al, bases, offsets, n_reads, out);
-	if (rc) return rc;
-	if ((rc = mmg_batch_run(al, *out)) || (rc = mmg_batch_fetch(al, *out))) { mmg_batch_destroy(*out); *out = 0; return rc; }
+	*out = 0;
+	CK(cudaSetDevice(al->device));
+	for (uint32_t i = 0; i < n_reads; ++i) {
+		uint64_t l = offsets[i + 1] - offsets[i];
+		if (l > 0x7fffffffULL || l > al->cap_bases) { mmg_set_error("read %u is longer than the chunk capacity (%llu bases)", i, (unsigned long long)al->cap_bases); return MMG_EINVAL; }
+	}
+	mmg_batch *b = new mmg_batch();
+	b->n_reads = n_reads, b->h_bases = bases, b->h_off = offsets;
+	b->n_bases = n_reads ? offsets[n_reads] - offsets[0] : 0;
+	b->off.resize((size_t)n_reads + 1);
+	for (uint32_t i = 0; i <= n_reads; ++i) b->off[i] = offsets[i] - offsets[0];
+	b->d_bases = 0, b->d_off = 0, b->d_hits = 0, b->d_nregs = 0, b->d_stats = 0, b->d_cigar = 0, b->cigar_cap = 0, b->n_cigar_dev = 0;
+	b->hits_cap = 0, b->n_hits_dev = 0;
+	b->uploaded = b->ran = b->fetched = false;
+	b->streamed = true;
+	b->dbg_r0 = b->dbg_r1 = 0;
+	memset(b->stats, 0, sizeof(b->stats));
+	int rc = map_batch_streamed(al, b);
+	if (rc) {
+		cudaStreamSynchronize(al->stream), cudaStreamSynchronize(al->s_in), cudaStreamSynchronize(al->s_out);
+		mmg_batch_destroy(b);
+		return rc;
+	}
+	*out = b;
 	return MMG_OK;
 }
 

@@ -27,23 +27,33 @@ __device__ __forceinline__ bool key_gt(uint64_t xa, uint32_t ia, uint64_t xb, ui
 	return xa > xb || (xa == xb && ia > ib);
 }
 
+/* ELEMS = shared-memory tile (records).  The SMALL instantiation keeps many CTAs resident per SM
+ * (the per-read chain of dependent global loads is latency, not bandwidth) and defers reads that
+ * do not fit its tile to big_list; the BIG instantiation (LIST = true) takes its reads from there. */
+template<int ELEMS, bool LIST>
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work)
+sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work, uint32_t *big_list, uint32_t *n_big)
 {
 	MMG_DYN_SMEM(smem_raw);
 	__shared__ uint32_t s_item;
 	__shared__ int s_tie;
 	__shared__ int s_bkt[512];
 	uint64_t *sx = (uint64_t*)smem_raw;
-	uint32_t *si = (uint32_t*)(sx + SORT_SMEM_ELEMS);
+	uint32_t *si = (uint32_t*)(sx + ELEMS);
 	const int tid = threadIdx.x, nt = blockDim.x;
+	const uint32_t n_items = LIST ? *n_big : r1 - r0;
 
 	for (;;) {
 		if (tid == 0) s_item = atomicAdd(work, 1u), s_tie = 0;
 		__syncthreads();
-		const uint32_t r = r0 + s_item;
-		if (r >= r1) break;
+		if (s_item >= n_items) break;
+		const uint32_t r = LIST ? big_list[s_item] : r0 + s_item;
 		const int n = (int)c.n_a[r];
+		if (!LIST && n > ELEMS) { /* uniform over the CTA */
+			if (tid == 0) big_list[atomicAdd(n_big, 1u)] = r;
+			__syncthreads();
+			continue;
+		}
 		const uint64_t ab = c.a_off[r] - c.a_off0;
 		const uint64_t *ax = c.ax + ab, *ay = c.ay + ab;
 		uint64_t *bx = c.bx + ab, *by = c.by + ab;
@@ -52,7 +62,7 @@ sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work)
 			while (m < n) m <<= 1;
 			uint64_t *kx;
 			uint32_t *ki;
-			if (m <= SORT_SMEM_ELEMS) kx = sx, ki = si;
+			if (m <= ELEMS) kx = sx, ki = si;
 			else kx = c.zx + 2 * ab, ki = (uint32_t*)(c.zy + 2 * ab); /* global tile: m < 2n */
 			for (int i = tid; i < m; i += nt) kx[i] = i < n ? ax[i] : MMG_INF64, ki[i] = (uint32_t)i;
 			__syncthreads();
@@ -94,12 +104,17 @@ sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work)
 
 int launch_sort(const ChunkDev &c, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work)
 {
-	size_t smem = (size_t)SORT_SMEM_ELEMS * 12;
+	/* work[0]: read counter of the small pass, work[1]: length of big_list, work[2]: list counter of the big pass */
+	const size_t smem_big = (size_t)SORT_SMEM_ELEMS * 12, smem_small = (size_t)SORT_SMALL_ELEMS * 12;
 	static bool attr_done = false;
-	if (!attr_done) { cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
-	int grid = n_sms * 2, need = (int)(r1 - r0);
+	if (!attr_done) { cudaFuncSetAttribute(sort_kernel<SORT_SMEM_ELEMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big); attr_done = true; }
+	int grid = n_sms * 8, need = (int)(r1 - r0);
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
-	MMG_LAUNCH(sort_kernel, grid, SORT_THREADS, smem, st, c, r0, r1, work);
+	MMG_LAUNCH((sort_kernel<SORT_SMALL_ELEMS, false>), grid, SORT_THREADS, smem_small, st, c, r0, r1, work, c.big_list, work + 1);
+	grid = n_sms * 2;
+	if (grid > need) grid = need;
+	if (grid < 1) grid = 1;
+	MMG_LAUNCH((sort_kernel<SORT_SMEM_ELEMS, true>), grid, SORT_THREADS, smem_big, st, c, r0, r1, work + 2, c.big_list, work + 1);
 	return 0;
 }

@@ -8,6 +8,7 @@
 #define CHAIN_WARPS 4
 #define SORT_THREADS 256
 #define SORT_SMEM_ELEMS 8192
+#define SORT_SMALL_ELEMS 2048
 
 enum { ST_H2D = 0, ST_SKETCH, ST_SEED, ST_SCAN, ST_EXPAND, ST_SORT, ST_CHAIN, ST_BACKTRACK, ST_RECHAIN, ST_REGS, ST_EXTEND, ST_D2H };
 

@@ -170,3 +170,20 @@ def test_cigar_mode_fixture_map_one(emu_lib, oracle_mod):
         assert all([(int(x) >> 4, int(x) & 15) for x in dev.hit_cigar(h)] == [(400, 0)] for h in dev.hits)
     finally:
         c.close()
+
+
+def test_long_reads_use_large_tiles(emu_lib, oracle_mod):
+    """Reads whose anchors exceed the small shared-memory tiles (sort: 2048 records) take the
+    deferred large-tile passes; results must not change."""
+    ref, coff, names, seqs = parity.random_reference(81, [200000])
+    c = parity.Case(emu_lib, names, seqs)
+    try:
+        buf, offs, _ = data_gen.make_reads(82, ref, coff, 6, 20000, 60000, p_sub=0.01, p_ins=0.005, p_del=0.005)
+        buf2, offs2, _ = data_gen.make_reads(83, ref, coff, 20, 300, 3000)
+        buf = np.concatenate([buf2, buf]); offs = np.concatenate([offs2, offs[1:] + offs2[-1]])
+        dev, stage_diffs = parity.compare_stages(c, buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert ora.stats["n_anchor"] > 6 * 2048
+        assert stage_diffs == [] and parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
+    finally:
+        c.close()
