@@ -85,6 +85,9 @@ struct ChunkDev {
 	const char *seq;          /* concatenated ASCII bases */
 	const uint64_t *off;      /* n_reads + 1: absolute offsets into seq */
 	uint64_t off0;            /* off[0]: per-read slices of the base-sized arrays start at off[r] - off0 */
+	const uint64_t *seg_beg;  /* segment mode of the sketch kernel (index construction), else 0 */
+	const uint32_t *seg_len;
+	uint32_t seg_cap;
 	/* sketch */
 	uint64_t *mz_x; uint32_t *mz_y; uint32_t *n_mz;
 	/* seeds */

@@ -15,44 +15,65 @@
 #define MMG_DEV_SORT_CUH
 #include "dev_common.cuh"
 
-__device__ __forceinline__ void dev_insertsort_128x(uint64_t *x, uint64_t *y, int beg, int end)
+template<typename YT>
+__device__ __forceinline__ void dev_insertsort_t(uint64_t *x, YT *y, int beg, int end)
 {
 	for (int i = beg + 1; i < end; ++i)
 		if (x[i] < x[i - 1]) {
-			uint64_t tx = x[i], ty = y[i];
+			uint64_t tx = x[i];
+			YT ty = y[i];
 			int j;
 			for (j = i; j > beg && tx < x[j - 1]; --j) x[j] = x[j - 1], y[j] = y[j - 1];
 			x[j] = tx, y[j] = ty;
 		}
 }
 
-/* bkt: 512 ints of scratch (bucket begin/end); stk: 3 ints per pending range, at least 3*(n/65+1) ints */
-static __device__ void dev_radix_sort_128x(uint64_t *x, uint64_t *y, int n, int *bkt, int *stk)
+/* bkt: 512 ints of scratch (bucket begin/end); stk: 3 ints per pending range, at least 3*(n/65+1) ints.
+ * LEAF_SORT = false stops before the insertion sorts of the leaf ranges (<= 64 elements): those are stable,
+ * so the caller may finish with ANY stable sort of the whole array by key (the leaves are disjoint, contiguous
+ * and already in key order relative to each other) - sort.cu does that with the whole CTA.
+ * A pass in which every element of the range has the same key byte moves nothing; it is detected after the
+ * counting loop and skipped.  Bucket loops only span the byte values that occur. */
+template<typename YT, bool LEAF_SORT>
+static __device__ void dev_radix_sort_t(uint64_t *x, YT *y, int n, int *bkt, int *stk)
 {
-	if (n <= 64) { dev_insertsort_128x(x, y, 0, n); return; }
+	if (n <= 64) { if (LEAF_SORT) dev_insertsort_t(x, y, 0, n); return; }
 	int *bb = bkt, *be = bkt + 256;
 	uint64_t diff = 0;
 	for (int i = 1; i < n; ++i) diff |= x[i] ^ x[0];
 	if (diff == 0) return;
 	int s0 = ((63 - __clzll((long long)diff)) >> 3) << 3; /* highest key byte that differs */
 	int sp = 0;
+	for (int k = 0; k < 256; ++k) be[k] = 0;
 	stk[0] = 0, stk[1] = n, stk[2] = s0, sp = 1;
 	while (sp > 0) {
 		--sp;
-		const int beg = stk[3 * sp], end = stk[3 * sp + 1], s = stk[3 * sp + 2];
-		for (int k = 0; k < 256; ++k) be[k] = 0;
-		for (int i = beg; i < end; ++i) ++be[(x[i] >> s) & 255];
+		const int beg = stk[3 * sp], end = stk[3 * sp + 1];
+		int s = stk[3 * sp + 2];
+		int kmin, kmax;
+		for (;;) { /* be[] is all zero here */
+			kmin = 255, kmax = 0;
+			for (int i = beg; i < end; ++i) {
+				int b = (int)((x[i] >> s) & 255);
+				++be[b];
+				kmin = b < kmin ? b : kmin, kmax = b > kmax ? b : kmax;
+			}
+			if (kmin != kmax || s == 0) break;
+			be[kmin] = 0, s -= 8;           /* one bucket holds the whole range: nothing moves, next byte */
+		}
 		{
 			int pos = beg;
-			for (int k = 0; k < 256; ++k) { int cnt = be[k]; bb[k] = pos; pos += cnt; be[k] = pos; }
+			for (int k = kmin; k <= kmax; ++k) { int cnt = be[k]; bb[k] = pos; pos += cnt; be[k] = pos; }
 		}
-		for (int k = 0; k < 256;) {
+		for (int k = kmin; k <= kmax;) {
 			if (bb[k] != be[k]) {
 				int l = (int)((x[bb[k]] >> s) & 255);
 				if (l != k) {
-					uint64_t tx = x[bb[k]], ty = y[bb[k]];
+					uint64_t tx = x[bb[k]];
+					YT ty = y[bb[k]];
 					do {
-						uint64_t sx = tx, sy = ty;
+						uint64_t sx = tx;
+						YT sy = ty;
 						int q = bb[l]++;
 						tx = x[q], ty = y[q];
 						x[q] = sx, y[q] = sy;
@@ -63,17 +84,25 @@ static __device__ void dev_radix_sort_128x(uint64_t *x, uint64_t *y, int n, int 
 				} else ++bb[k];
 			} else ++k;
 		}
-		if (s) {
+		{
 			const int s2 = s > 8 ? s - 8 : 0;
 			int start = beg;
-			for (int k = 0; k < 256; ++k) {
+			for (int k = kmin; k <= kmax; ++k) {
 				int e = be[k], sz = e - start;
-				if (sz > 64) stk[3 * sp] = start, stk[3 * sp + 1] = e, stk[3 * sp + 2] = s2, ++sp;
-				else if (sz > 1) dev_insertsort_128x(x, y, start, e);
+				be[k] = 0;
+				if (s) {
+					if (sz > 64) stk[3 * sp] = start, stk[3 * sp + 1] = e, stk[3 * sp + 2] = s2, ++sp;
+					else if (LEAF_SORT && sz > 1) dev_insertsort_t(x, y, start, e);
+				}
 				start = e;
 			}
 		}
 	}
+}
+
+static __device__ void dev_radix_sort_128x(uint64_t *x, uint64_t *y, int n, int *bkt, int *stk)
+{
+	dev_radix_sort_t<uint64_t, true>(x, y, n, bkt, stk);
 }
 
 #endif

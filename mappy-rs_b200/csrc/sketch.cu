@@ -26,70 +26,118 @@
 #include "dev_common.cuh"
 #include "stages.h"
 
-__device__ __forceinline__ uint64_t dev_hash64(uint64_t key, uint64_t mask)
-{
-	key = (~key + (key << 21)) & mask;
-	key = key ^ key >> 24;
-	key = ((key + (key << 3)) + (key << 8)) & mask;
-	key = key ^ key >> 14;
-	key = ((key + (key << 2)) + (key << 4)) & mask;
-	key = key ^ key >> 28;
-	key = (key + (key << 31)) & mask;
-	return key;
-}
+template<typename KT> struct SkKey;
+/* k <= 15: a k-mer and its hash fit 30 bits, every step is 32-bit arithmetic (hash64 restricted to 2k <= 30
+ * bits only ever reads the low 2k bits of its intermediates, so the 32-bit evaluation is bit-identical) */
+template<> struct SkKey<uint32_t> {
+	static __device__ __forceinline__ uint32_t inf() { return 0xffffffffu; }
+	static __device__ __forceinline__ uint32_t hash(uint32_t key, uint32_t mask)
+	{
+		key = (~key + (key << 21)) & mask;
+		key = key ^ key >> 24;
+		key = ((key + (key << 3)) + (key << 8)) & mask;
+		key = key ^ key >> 14;
+		key = ((key + (key << 2)) + (key << 4)) & mask;
+		key = key ^ key >> 28;
+		key = (key + (key << 31)) & mask;
+		return key;
+	}
+	/* bits [s2, s2 + 32) of the 128-bit register (Whi:Wlo), s2 <= 62 */
+	static __device__ __forceinline__ uint32_t cut(uint64_t Wlo, uint64_t Whi, int s2, uint32_t mask)
+	{
+		const uint32_t w0 = (uint32_t)Wlo, w1 = (uint32_t)(Wlo >> 32), w2 = (uint32_t)Whi;
+		const bool up = s2 >= 32;
+		return __funnelshift_r(up ? w1 : w0, up ? w2 : w1, (uint32_t)s2 & 31u) & mask;
+	}
+	static __device__ __forceinline__ uint32_t revcomp(uint32_t v, int k)
+	{
+		uint32_t r = __brev(v);
+		r = ((r & 0xaaaaaaaau) >> 1) | ((r & 0x55555555u) << 1);
+		return ~r >> (32 - 2 * k);
+	}
+};
+template<> struct SkKey<uint64_t> {
+	static __device__ __forceinline__ uint64_t inf() { return MMG_INF64; }
+	static __device__ __forceinline__ uint64_t hash(uint64_t key, uint64_t mask)
+	{
+		key = (~key + (key << 21)) & mask;
+		key = key ^ key >> 24;
+		key = ((key + (key << 3)) + (key << 8)) & mask;
+		key = key ^ key >> 14;
+		key = ((key + (key << 2)) + (key << 4)) & mask;
+		key = key ^ key >> 28;
+		key = (key + (key << 31)) & mask;
+		return key;
+	}
+	static __device__ __forceinline__ uint64_t cut(uint64_t Wlo, uint64_t Whi, int s2, uint64_t mask)
+	{
+		return ((Wlo >> s2) | (s2 ? Whi << (64 - s2) : 0)) & mask;
+	}
+	static __device__ __forceinline__ uint64_t revcomp(uint64_t v, int k)
+	{
+		uint64_t r = __brevll(v);
+		r = ((r & 0xaaaaaaaaaaaaaaaaULL) >> 1) | ((r & 0x5555555555555555ULL) << 1);
+		return ~r >> (64 - 2 * k);
+	}
+};
 
+/* A,C,G,T/U (either case) -> 0..3, anything else 4 */
 __device__ __forceinline__ int dev_nt4(unsigned c)
 {
-	unsigned u = c & 0xdfu;
-	return u == 'A' ? 0 : u == 'C' ? 1 : u == 'G' ? 2 : (u == 'T' || u == 'U') ? 3 : 4;
+	const unsigned d = (c & 0xdfu) - 'A';
+	const bool ok = d < 21u && ((0x180045u >> d) & 1u);
+	unsigned code = (c >> 1) & 3u;
+	code ^= code >> 1;
+	return ok ? (int)code : 4;
 }
 
-/* reverse complement of the k 2-bit bases in the low 2k bits of v */
-__device__ __forceinline__ uint64_t dev_revcomp(uint64_t v, int k)
-{
-	uint64_t r = __brevll(v);
-	r = ((r & 0xaaaaaaaaaaaaaaaaULL) >> 1) | ((r & 0x5555555555555555ULL) << 1);
-	r = ~r;
-	return r >> (64 - 2 * k);
-}
-
-template<int RING>
+/* The ring holds, per event, the hash (KT; all-ones = no usable k-mer), y = pos<<1|strand and l.
+ * Read mode: read r is c.seq[c.off[r] .. c.off[r+1]), records go to the read's base offset.
+ * Segment mode (c.seg_beg != 0; index construction): segment r is c.seq[seg_beg[r] .. +seg_len[r]), records go to
+ * slot r * c.seg_cap. */
+template<int RING, typename KT>
 __global__ void __launch_bounds__(SKETCH_WARPS * 32)
 sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 {
 	MMG_DYN_SMEM(smem_raw);
+	typedef SkKey<KT> K;
 	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
 	const uint32_t RM = RING - 1;
-	uint64_t *xr = (uint64_t*)smem_raw + (size_t)wib * RING;
-	uint32_t *yr = (uint32_t*)((uint64_t*)smem_raw + (size_t)SKETCH_WARPS * RING) + (size_t)wib * RING;
-	uint32_t *lr = (uint32_t*)((uint64_t*)smem_raw + (size_t)SKETCH_WARPS * RING) + (size_t)SKETCH_WARPS * RING + (size_t)wib * RING;
-	const uint64_t mask = (1ULL << 2 * k) - 1;
+	KT *xr = (KT*)smem_raw + (size_t)wib * RING;
+	uint32_t *yr = (uint32_t*)((KT*)smem_raw + (size_t)SKETCH_WARPS * RING) + (size_t)wib * RING;
+	uint32_t *lr = (uint32_t*)((KT*)smem_raw + (size_t)SKETCH_WARPS * RING) + (size_t)SKETCH_WARPS * RING + (size_t)wib * RING;
+	const KT mask = (KT)(((uint64_t)1 << 2 * k) - 1), INF = K::inf();
 	const uint32_t lt = mmg_lanemask_lt();
 	unsigned long long tot_mz = 0, tot_bases = 0;
 
 	for (;;) {
 		uint32_t r = mmg_next_item(work);
 		if (r >= c.n_reads) break;
-		const uint64_t base = c.off[r] - c.off0;
-		const int len = (int)(c.off[r + 1] - c.off[r]);
-		const char *s = c.seq + c.off[r];
+		uint64_t base;
+		int len;
+		const char *s;
+		if (c.seg_beg) base = (uint64_t)r * c.seg_cap, len = (int)c.seg_len[r], s = c.seq + c.seg_beg[r];
+		else base = c.off[r] - c.off0, len = (int)(c.off[r + 1] - c.off[r]), s = c.seq + c.off[r];
 		uint64_t *ox = c.mz_x + base;
 		uint32_t *oy = c.mz_y + base;
 
-		for (int j = lane; j < RING; j += 32) xr[j] = MMG_INF64;
+		for (int j = lane; j < RING; j += 32) xr[j] = INF;
 		__syncwarp();
 
 		uint64_t prev = 0;          /* last 32 usable bases, newest in the low bits */
 		int nvalid = 0;             /* usable bases so far */
 		int e_base = 0;             /* events so far */
 		int lastN = -1;             /* event index of the last ambiguous base */
-		int pidx = -1; uint64_t px = MMG_INF64; /* selection after the last event */
+		int pidx = -1; KT px = INF; /* selection after the last event */
 		int n_out = 0;
+		unsigned ch = lane < len ? (unsigned char)s[lane] : 0u;
 
 		for (int pos0 = 0; pos0 < len; pos0 += 32) {
 			const int i = pos0 + lane;
 			const bool inb = i < len;
-			const int cc = inb ? dev_nt4((unsigned char)s[i]) : 4;
+			const unsigned ch_next = i + 32 < len ? (unsigned char)s[i + 32] : 0u; /* in flight while this step computes */
+			const int cc = inb ? dev_nt4(ch) : 4;
+			ch = ch_next;
 			const bool valid = inb && cc < 4, isN = inb && cc == 4;
 			const uint32_t vmask = __ballot_sync(MMG_FULL, valid);
 			const int nv = __popc(vmask), ci = __popc(vmask & lt);
@@ -102,8 +150,8 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 			const uint64_t Wlo = sh == 64 ? cur : sh == 0 ? prev : (prev << sh) | cur;
 			const uint64_t Whi = sh == 64 ? prev : sh == 0 ? 0 : prev >> (64 - sh);
 			const int s2 = valid ? 2 * (nv - 1 - ci) : 0;
-			const uint64_t fwd = ((Wlo >> s2) | (s2 ? Whi << (64 - s2) : 0)) & mask;
-			const uint64_t rev = dev_revcomp(fwd, k);
+			const KT fwd = K::cut(Wlo, Whi, s2, mask);
+			const KT rev = K::revcomp(fwd, k);
 			/* a k-mer assembled from fewer than k usable bases can never equal its
 			 * (zero-filled) reverse upstream, so the symmetric test starts at k bases */
 			const bool pal = valid && (nvalid + ci + 1 >= k) && fwd == rev;
@@ -117,11 +165,11 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 			}
 			const int l = isN ? 0 : ei - lastN_e;
 			if (isev) {
-				uint64_t x = MMG_INF64;
+				KT x = INF;
 				uint32_t y = 0;
 				if (!isN && l >= k) {
 					int z = fwd < rev ? 0 : 1;
-					x = dev_hash64(z ? rev : fwd, mask) << 8 | (uint64_t)k;
+					x = K::hash(z ? rev : fwd, mask);
 					y = (uint32_t)i << 1 | (uint32_t)z;
 				}
 				xr[ei & RM] = x, yr[ei & RM] = y, lr[ei & RM] = (uint32_t)l;
@@ -135,35 +183,37 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 			/* ---- window minimum + emission: lane t owns event e_base + t ---- */
 			const bool act = lane < n_ev;
 			const int e = e_base + lane;
-			uint64_t xe = MMG_INF64, bxv = MMG_INF64;
-			int le = 0, bj = e;
+			KT xe = INF, bxv = INF;
+			int le = 0, bj = e, neq = 0;
 			if (act) {
 				xe = xr[e & RM], le = (int)lr[e & RM];
-				for (int j = e - w + 1; j <= e; ++j) {      /* P(e): newest among equal keys */
-					uint64_t vx = xr[j & RM];
-					if (bxv >= vx) bxv = vx, bj = j;
+				for (int j = e - w + 1; j <= e; ++j) {      /* P(e): newest among equal keys; neq = copies of it in the window */
+					const KT vx = xr[j & RM];
+					const bool less = vx < bxv, same = vx == bxv;
+					neq = less ? 1 : neq + (same ? 1 : 0);
+					if (less || same) bxv = vx, bj = j;
 				}
 			}
-			uint64_t pmx = __shfl_up_sync(MMG_FULL, bxv, 1);
+			KT pmx = __shfl_up_sync(MMG_FULL, bxv, 1);
 			int pmi = __shfl_up_sync(MMG_FULL, bj, 1);
 			if (lane == 0) pmx = px, pmi = pidx;
-			const bool caseA = act && le == w + k - 1 && pmx != MMG_INF64;
+			const bool caseA = act && le == w + k - 1 && pmx != INF;
 			const bool caseB = act && xe <= pmx;
 			const bool caseC = act && !caseB && pmi == e - w;
-			const bool emitB = caseB && le >= w + k && pmx != MMG_INF64;
+			const bool emitB = caseB && le >= w + k && pmx != INF;
 			const bool emitC = caseC && le >= w + k - 1;
-			const bool dupC = emitC && bxv != MMG_INF64;
+			const bool dupC = emitC && bxv != INF && neq > 1;
 			int cnt = (emitB || emitC) ? 1 : 0;
 			if (caseA) for (int j = e - w + 1; j < e; ++j) cnt += (xr[j & RM] == pmx && j != pmi);
-			if (dupC) for (int j = e - w + 1; j <= e; ++j) cnt += (xr[j & RM] == bxv && j != bj);
+			if (dupC) cnt += neq - 1;
 			int tot, o = mmg_warp_excl_scan(cnt, &tot);
 			if (cnt) {
 				o += n_out;
 				if (caseA) for (int j = e - w + 1; j < e; ++j)
-					if (xr[j & RM] == pmx && j != pmi) ox[o] = xr[j & RM], oy[o] = yr[j & RM], ++o;
-				if (emitB || emitC) ox[o] = xr[pmi & RM], oy[o] = yr[pmi & RM], ++o;
+					if (xr[j & RM] == pmx && j != pmi) ox[o] = (uint64_t)xr[j & RM] << 8 | (uint64_t)k, oy[o] = yr[j & RM], ++o;
+				if (emitB || emitC) ox[o] = (uint64_t)xr[pmi & RM] << 8 | (uint64_t)k, oy[o] = yr[pmi & RM], ++o;
 				if (dupC) for (int j = e - w + 1; j <= e; ++j)
-					if (xr[j & RM] == bxv && j != bj) ox[o] = xr[j & RM], oy[o] = yr[j & RM], ++o;
+					if (xr[j & RM] == bxv && j != bj) ox[o] = (uint64_t)xr[j & RM] << 8 | (uint64_t)k, oy[o] = yr[j & RM], ++o;
 			}
 			n_out += tot;
 			if (n_ev > 0) {
@@ -174,17 +224,28 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 			__syncwarp();
 		}
 		if (lane == 0) {
-			if (px != MMG_INF64) ox[n_out] = xr[pidx & RM], oy[n_out] = yr[pidx & RM], ++n_out;
+			if (px != INF) ox[n_out] = (uint64_t)xr[pidx & RM] << 8 | (uint64_t)k, oy[n_out] = yr[pidx & RM], ++n_out;
 			c.n_mz[r] = (uint32_t)n_out;
 		}
 		n_out = __shfl_sync(MMG_FULL, n_out, 0);
 		tot_mz += n_out, tot_bases += len;
 		__syncwarp();
 	}
-	if (lane == 0 && tot_bases) {
+	if (lane == 0 && tot_bases && c.stats) {
 		atomicAdd(&c.stats[0], tot_bases);
 		atomicAdd(&c.stats[1], tot_mz);
 	}
+}
+
+template<int RING, typename KT>
+static void launch_sketch_t(const ChunkDev &c, int w, int k, int grid, cudaStream_t st, uint32_t *work)
+{
+	size_t smem = (size_t)SKETCH_WARPS * RING * (sizeof(KT) + 8);
+	if (smem > 48 * 1024) {
+		static bool attr_done = false;
+		if (!attr_done) { cudaFuncSetAttribute(sketch_kernel<RING, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+	}
+	MMG_LAUNCH((sketch_kernel<RING, KT>), grid, SKETCH_WARPS * 32, smem, st, c, w, k, work);
 }
 
 int launch_sketch(const ChunkDev &c, const DevIndex &di, int n_sms, cudaStream_t st, uint32_t *work)
@@ -195,13 +256,11 @@ int launch_sketch(const ChunkDev &c, const DevIndex &di, int n_sms, cudaStream_t
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
 	if (w <= 32) {
-		size_t smem = (size_t)SKETCH_WARPS * 64 * 16;
-		MMG_LAUNCH(sketch_kernel<64>, grid, SKETCH_WARPS * 32, smem, st, c, w, k, work);
+		if (k <= 15) launch_sketch_t<64, uint32_t>(c, w, k, grid, st, work);
+		else launch_sketch_t<64, uint64_t>(c, w, k, grid, st, work);
 	} else {
-		size_t smem = (size_t)SKETCH_WARPS * 512 * 16;
-		static bool attr_done = false;
-		if (!attr_done) { cudaFuncSetAttribute(sketch_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
-		MMG_LAUNCH(sketch_kernel<512>, grid, SKETCH_WARPS * 32, smem, st, c, w, k, work);
+		if (k <= 15) launch_sketch_t<512, uint32_t>(c, w, k, grid, st, work);
+		else launch_sketch_t<512, uint64_t>(c, w, k, grid, st, work);
 	}
 	return 0;
 }

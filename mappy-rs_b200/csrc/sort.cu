@@ -62,38 +62,59 @@ sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work, uint32_t *big_
 			while (m < n) m <<= 1;
 			uint64_t *kx;
 			uint32_t *ki;
-			if (m <= ELEMS) kx = sx, ki = si;
+			const bool in_smem = m <= ELEMS;
+			if (in_smem) kx = sx, ki = si;
 			else kx = c.zx + 2 * ab, ki = (uint32_t*)(c.zy + 2 * ab); /* global tile: m < 2n */
-			for (int i = tid; i < m; i += nt) kx[i] = i < n ? ax[i] : MMG_INF64, ki[i] = (uint32_t)i;
-			__syncthreads();
-			for (int k = 2; k <= m; k <<= 1) {
-				for (int j = k >> 1; j > 0; j >>= 1) {
-					for (int t = tid; t < (m >> 1); t += nt) {
-						int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); /* index with bit j clear */
-						int p = i | j;
-						bool up = (i & k) == 0;
-						uint64_t xa = kx[i], xb = kx[p];
-						uint32_t ia = ki[i], ib = ki[p];
-						if (key_gt(xa, ia, xb, ib) == up) kx[i] = xb, ki[i] = ib, kx[p] = xa, ki[p] = ia;
+			const uint64_t *srcx = ax, *srcy = ay;
+			for (int pass = 0; pass < 2; ++pass) {
+				for (int i = tid; i < m; i += nt) kx[i] = i < n ? srcx[i] : MMG_INF64, ki[i] = (uint32_t)i;
+				__syncthreads();
+				for (int k = 2; k <= m; k <<= 1) {
+					for (int j = k >> 1; j > 0; j >>= 1) {
+						for (int t = tid; t < (m >> 1); t += nt) {
+							int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); /* index with bit j clear */
+							int p = i | j;
+							bool up = (i & k) == 0;
+							uint64_t xa = kx[i], xb = kx[p];
+							uint32_t ia = ki[i], ib = ki[p];
+							if (key_gt(xa, ia, xb, ib) == up) kx[i] = xb, ki[i] = ib, kx[p] = xa, ki[p] = ia;
+						}
+						__syncthreads();
 					}
-					__syncthreads();
 				}
-			}
-			int tie = 0;
-			for (int i = tid; i < n; i += nt) {
-				uint64_t x = kx[i];
-				bx[i] = x, by[i] = ay[ki[i]];
-				if (i + 1 < n && kx[i + 1] == x) tie = 1;
-			}
-			if (tie && n > 64) s_tie = 1;
-			__syncthreads();
-			if (s_tie) { /* replay upstream's unstable permutation from the unsorted input */
-				for (int i = tid; i < n; i += nt) bx[i] = ax[i], by[i] = ay[i];
+				int tie = 0;
+				for (int i = tid; i < n; i += nt) {
+					uint64_t x = kx[i];
+					bx[i] = x, by[i] = srcy[ki[i]];
+					if (i + 1 < n && kx[i + 1] == x) tie = 1;
+				}
+				if (pass == 0 && tie && n > 64) s_tie = 1;
+				__syncthreads();
+				if (pass == 1 || !s_tie) break;
+				/* Equal keys in a read above upstream's insertion-sort size: the order upstream's unstable
+				 * radix sort leaves them in is replayed.  One thread runs the radix passes over (key, source
+				 * index) in the tile; the insertion sorts of the leaf ranges are stable, so they are replaced
+				 * by a second run of the network on (key, position after the radix passes). */
+				if (!in_smem) { /* the global tile is the scratch the second pass would need: serial replay */
+					for (int i = tid; i < n; i += nt) bx[i] = ax[i], by[i] = ay[i];
+					__syncthreads();
+					if (tid == 0) {
+						dev_radix_sort_128x(bx, by, n, s_bkt, c.f + ab);
+						c.flags[r] |= 1u;
+					}
+					break;
+				}
+				for (int i = tid; i < n; i += nt) kx[i] = ax[i], ki[i] = (uint32_t)i;
 				__syncthreads();
 				if (tid == 0) {
-					dev_radix_sort_128x(bx, by, n, s_bkt, c.f + ab);
+					dev_radix_sort_t<uint32_t, false>(kx, ki, n, s_bkt, c.f + ab);
 					c.flags[r] |= 1u;
 				}
+				__syncthreads();
+				uint64_t *zx = c.zx + 2 * ab, *zy = c.zy + 2 * ab;
+				for (int i = tid; i < n; i += nt) zx[i] = kx[i], zy[i] = ay[ki[i]];
+				__syncthreads();
+				srcx = zx, srcy = zy;
 			}
 		} else if (n == 1) {
 			if (tid == 0) bx[0] = ax[0], by[0] = ay[0];

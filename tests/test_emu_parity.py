@@ -187,3 +187,37 @@ def test_long_reads_use_large_tiles(emu_lib, oracle_mod):
         assert stage_diffs == [] and parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
     finally:
         c.close()
+
+
+def _dup_reads(ref, n, seed):
+    """Reads with a tandem duplication: two query minimizers hit the SAME target position, i.e. equal anchor keys."""
+    rs = np.random.RandomState(seed)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    out = []
+    for _ in range(n):
+        a = int(rs.randint(0, len(ref) - 9000))
+        l1, d = int(rs.randint(1500, 6000)), int(rs.randint(200, 1200))
+        s = np.concatenate([ref[a:a + l1], ref[a + d:a + l1]])
+        if rs.rand() < 0.5:
+            s = np.array([comp[int(c)] for c in s[::-1]], dtype=np.uint8)
+        out.append(s.tobytes().decode())
+    return out
+
+
+def test_equal_anchor_keys_replay_upstream_order(emu_lib, oracle_mod):
+    """Equal anchor keys above 64 anchors: the order left by upstream's unstable radix sort reaches the
+    chaining DP, so the sort stage must reproduce it (sort.cu tie path)."""
+    ref, coff, names, seqs = parity.random_reference(91, [120000])
+    c = parity.Case(emu_lib, names, seqs)
+    try:
+        buf, offs = oracle_mod.pack_reads(_dup_reads(ref, 24, 92))
+        n_tie = 0
+        for i in range(len(offs) - 1):
+            x = c.oracle.trace(buf[int(offs[i]):int(offs[i + 1])].tobytes())["a_sorted"]["x"]
+            n_tie += int(len(x) > 64 and (np.diff(x) == 0).any())
+        assert n_tie >= 20
+        dev, stage_diffs = parity.compare_stages(c, buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert stage_diffs == [] and parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
+    finally:
+        c.close()
