@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- reads/s of the minimap2 mapping path behind mappy-rs `map_batch` on B200.
 
-Workload (BASELINE.json configs[1]): 5 Mb synthetic reference (seed 1), 200 000
+Default workload (BASELINE.json configs[1]): 5 Mb synthetic reference (seed 1), 200 000
 simulated ONT reads of 1-10 kb with 8 % errors (seed 2), preset map-ont,
 mapping-only, one GPU.  One "step" = one pass of the whole hot path (sketch ->
-seed -> sort -> chain -> select/mapq) over the batch.
+seed -> sort -> chain -> select/mapq) over the batch.  --workload human / prefix /
+hifi select configs[2] (3.1 Gb reference), configs[3] (400-base prefixes streamed in
+20k batches, with batch latency) and configs[4] (map-hifi); --cigar turns MM_F_CIGAR on.
 
   value     : reads/s with the reads already resident in HBM, timed by CUDA
               events on the library's stream around all kernels of a step.
@@ -80,25 +82,66 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def workload(n_reads, rank):
+WORKLOADS = {
+    # name: (description, reference builder, read simulator kwargs, preset, reads per GPU default)
+    "config1": "BASELINE.json configs[1]: 5 Mb synthetic reference (seed 1), simulated 1-10 kb ONT reads (3% sub, 2% ins, 3% del; seed 2), map-ont",
+    "human": "BASELINE.json configs[2]: 3.1 Gb synthetic reference (24 contigs, GRCh38-proportional, seed 3), simulated 1-10 kb ONT reads (3% sub, 2% ins, 3% del; seed 4), map-ont, index replicated per GPU, reads sharded",
+    "prefix": "BASELINE.json configs[3]: 400-base read prefixes streamed in batches of 20 000 (readfish-style), map-ont",
+    "hifi": "BASELINE.json configs[4]: simulated HiFi reads N(15 kb, 2 kb) clipped to [10 kb, 25 kb], 0.5% errors (seed 5), map-hifi",
+}
+
+
+def workload(args, rank):
+    """Returns (ref, coff, names, buf, offs, preset) for this rank's shard (weak scaling: args.reads per GPU)."""
     import data_gen
-    ref, coff, names = data_gen.config1_reference()
-    buf, offs, _ = data_gen.make_reads(2 + 1000 * rank, ref, coff, n_reads, 1000, 10000, p_sub=0.03, p_ins=0.02, p_del=0.03)
-    return ref, coff, names, buf, offs
+    big = args.workload == "human" or args.ref == "human"
+    if big:
+        ref, coff, names = data_gen.make_reference(3, data_gen.config2_contig_lens(args.ref_bases))
+    else:
+        ref, coff, names = data_gen.config1_reference()
+    seed = (4 if big else 2) + 1000 * rank
+    preset = None
+    if args.workload == "hifi":
+        buf, offs, _ = data_gen.make_reads(5 + 1000 * rank, ref, coff, args.reads, 10000, 25000, len_mean=15000.0, len_sd=2000.0, p_sub=0.002, p_ins=0.0015, p_del=0.0015)
+        preset = "map-hifi"
+    else:
+        buf, offs, _ = data_gen.make_reads(seed, ref, coff, args.reads, 1000, 10000, p_sub=0.03, p_ins=0.02, p_del=0.03)
+        if args.workload == "prefix":   # the first 400 bases of every read
+            ln = np.minimum(np.diff(offs.astype(np.int64)), 400)
+            noffs = np.zeros(len(offs), dtype=np.uint64)
+            noffs[1:] = np.cumsum(ln)
+            idx = np.repeat(offs[:-1].astype(np.int64) - noffs[:-1].astype(np.int64), ln) + np.arange(int(noffs[-1]))
+            buf, offs = buf[idx].copy(), noffs
+    return ref, coff, names, buf, offs, preset
+
+
+def contig_seqs(ref, coff, names):
+    return [ref[int(coff[i]):int(coff[i + 1])].tobytes() for i in range(len(names))]
+
+
+def make_oracle(args, ref, coff, names, preset):
+    import mm2oracle as mo
+    o = mo.Oracle(names=names, seqs=contig_seqs(ref, coff, names), preset=preset)
+    o.set_opt("flag", 4 if args.cigar else 0)
+    return o
+
+
+def workload_text(args, n_reads):
+    return "%s; %d reads per GPU, %s" % (WORKLOADS[args.workload], n_reads, "CIGAR on" if args.cigar else "mapping-only")
 
 
 def run_reference(args, rank, world):
     """CPU arm: the oracle (kind 'port') with every host thread, on a bounded sample per step."""
     if rank != 0:
         return
-    import mm2oracle as mo
-    n_sample = min(args.reads, args.cpu_sample)
-    ref, coff, names, buf, offs = workload(n_sample, 0)
-    o = mo.Oracle(names=names, seqs=[ref.tobytes()])
-    o.set_opt("flag", 4 if args.cigar else 0)
+    args.reads = min(args.reads, args.cpu_sample)
+    ref, coff, names, buf, offs, preset = workload(args, 0)
+    n_sample = len(offs) - 1
+    o = make_oracle(args, ref, coff, names, preset)
     cores = os.cpu_count() or 1
+    nw = min(2000, n_sample)
     for _ in range(args.warmup):
-        o.map_batch(buf[:int(offs[2000])], offs[:2001], cores)
+        o.map_batch(buf[:int(offs[nw])], offs[:nw + 1], cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         o.map_batch(buf, offs, cores)
@@ -109,10 +152,18 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "reads_per_s", "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic", "mbases_per_s": int(offs[-1]) / dt / 1e6,
-        "config": {"workload": "BASELINE.json configs[1]: 5 Mb synthetic reference, simulated 1-10 kb ONT reads (8% error), map-ont, mapping-only", "reads_per_step": n_sample},
+        "config": {"workload": workload_text(args, n_sample), "reads_per_step": n_sample},
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def load_traffic():
+    """dram bytes per launch of each stage kernel from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
 
 
 def run_ours(args, rank, local_rank, world):
@@ -125,12 +176,17 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _mmg.Lib()
-    ref, coff, names, buf, offs = workload(args.reads, rank)
+    ref, coff, names, buf, offs, preset = workload(args, rank)
     n_reads, n_bases = len(offs) - 1, int(offs[-1])
     io, mopt = _mmg.IdxOpt(), _mmg.MapOpt()
     lib.check(lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mopt)))
+    if preset:
+        lib.check(lib.L.mmg_set_opt(preset.encode(), ctypes.byref(io), ctypes.byref(mopt)))
     mopt.flag = 4 if args.cigar else 0  # configs[1] is mapping-only
-    idx = _mmg.Index.build(lib, io, names, [ref.tobytes()])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    idx = _mmg.Index.build(lib, io, names, contig_seqs(ref, coff, names), device=local_rank)
+    index_build_s = time.perf_counter() - t0
     lib.check(lib.L.mmg_mapopt_update(ctypes.byref(mopt), idx.h))
     al = _mmg.DeviceAligner(lib, idx, mopt, device=local_rank)
     al.set("profile", 1)
@@ -153,78 +209,113 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # batches of one step: the whole shard, or 20k-read batches in the streaming workload
+    if args.workload == "prefix":
+        cuts = list(range(0, n_reads, args.batch)) + [n_reads]
+    else:
+        cuts = [0, n_reads]
+    views = [(hptr[int(offs[a]):int(offs[b])], offs[a:b + 1] - offs[a]) for a, b in zip(cuts[:-1], cuts[1:])]
+
     # ---- device-resident timing -------------------------------------------------
-    b = al.upload(hptr, offs)
+    handles = [al.upload(v, o) for v, o in views]
     for _ in range(args.warmup):
-        al.run(b)
+        for b in handles:
+            al.run(b)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     dev_ms, stage_ms, launches = 0.0, {}, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        al.run(b)
-        dev_ms += al.last_run_ms()
-        for k, (ms, ln) in al.stage_times().items():
-            stage_ms[k] = stage_ms.get(k, 0.0) + ms
-            launches += ln
+        for b in handles:
+            al.run(b)
+            dev_ms += al.last_run_ms()
+            for k, (ms, ln) in al.stage_times().items():
+                stage_ms[k] = stage_ms.get(k, 0.0) + ms
+                launches += ln
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    al.fetch(b)
-    res = _mmg.Batch(lib, b, n_reads)
-    al.free(b)
+    stats = {}
+    res0 = None
+    for b, (v, o) in zip(handles, views):
+        al.fetch(b)
+        r = _mmg.Batch(lib, b, len(o) - 1)
+        res0 = res0 or r
+        for k, x in r.stats.items():
+            stats[k] = stats.get(k, 0) + x
+        al.free(b)
     dev_ms = maxrank(dev_ms)
     # ---- end to end through the C ABI with host buffers ---------------------------
     al.set("profile", 0)
     for _ in range(max(min(args.warmup, 2), 1)):
-        al.map_batch(hptr, offs)
+        for v, o in views:
+            al.map_batch(v, o)
     barrier()
+    lat = []
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
-        r = al.map_batch(hptr, offs)
-        d2h = r.hits.nbytes + r.cigar.nbytes + n_reads * 4 + 80
+        d2h = 0
+        for v, o in views:
+            t1 = time.perf_counter()
+            r = al.map_batch(v, o)
+            lat.append(time.perf_counter() - t1)
+            d2h += r.hits.nbytes + r.cigar.nbytes + (len(o) - 1) * 4 + 80
     barrier()
     e2e_s = maxrank((time.perf_counter() - t0) / args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    int_peak = al.int32_peak(local_rank) if rank == 0 else 0.0
     if rank != 0:
         return
-    stats = res.stats
     ms_per_step = dev_ms / args.steps
     value = world * n_reads / (ms_per_step / 1e3)
     stage_only = {k: v for k, v in stage_ms.items() if k in ALGO_BYTES and v > 0}
     top = max(stage_only, key=stage_only.get) if stage_only else "chain_dp"
-    top_ms = stage_only.get(top, 0.0) / args.steps
+    top_ms_step = stage_only.get(top, 0.0) / args.steps
     peak, how = measured_peak()
-    achieved = ALGO_BYTES[top](stats) / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
+    achieved = ALGO_BYTES[top](stats) / (top_ms_step / 1e3) / 1e9 if top_ms_step > 0 else 0.0
+    traffic = load_traffic().get(top)
     out = {
         "metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "mbases_per_s": world * n_bases / (ms_per_step / 1e3) / 1e6,
-        "config": {"workload": "BASELINE.json configs[1]: 5 Mb synthetic reference (seed 1), %d simulated 1-10 kb ONT reads (3%% sub, 2%% ins, 3%% del; seed 2), map-ont, %s" % (n_reads, "CIGAR on" if args.cigar else "mapping-only"),
-                   "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "l2": "inputs (%.0f MB) larger than L2" % (n_bases / 1e6), "parallelism": "reads sharded, index replicated"},
-        "e2e": {"value": world * n_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": n_bases + (n_reads + 1) * 8, "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+        "config": {"workload": workload_text(args, n_reads), "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "batches_per_step": len(views),
+                   "l2": "inputs (%.0f MB) larger than L2" % (n_bases / 1e6) if n_bases > 130e6 else "inputs %.0f MB; every step streams fresh per-chunk arenas (> L2) through all stages" % (n_bases / 1e6),
+                   "parallelism": "reads sharded, index replicated", "index_build_s": index_build_s, "index": "built on the device (index_dev.cu)"},
+        "e2e": {"value": world * n_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": n_bases + (n_reads + len(views)) * 8, "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                "mbases_per_s": world * n_bases / e2e_s / 1e6},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": "of " + how, "ms_per_launch": top_ms, "note": "integer/latency-bound stage; algorithmic bytes per BASELINE.md"},
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": "of " + how, "ms_per_step": top_ms_step,
+                     "note": "stage kernels are integer-issue / latency bound (DESIGN.md section 4); algorithmic bytes per BASELINE.md; achieved = bytes of all launches of the stage in a step / their summed event time"},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "counters": stats, "wall_ms_per_step": wall_ms / args.steps,
         "clocks": sampler.summary(),
     }
+    if int_peak > 0 and stats.get("n_iter"):
+        ch_ms = stage_ms.get("chain_dp", 0.0) / args.steps
+        if ch_ms > 0:
+            a = 24.0 * stats["n_iter"] / (ch_ms / 1e3) / 1e9
+            out["int32_roofline"] = {"kernel": "chain_dp", "achieved": a, "peak": int_peak, "unit": "Gop/s", "frac": a / int_peak,
+                                     "note": "24 int-ops per predecessor evaluation (BASELINE.md) over the measured INT32 IMAD/IADD3 issue peak of this GPU"}
+    if args.workload == "prefix":
+        ls = sorted(lat)
+        out["latency_ms"] = {"batch_reads": args.batch, "p50": 1e3 * ls[len(ls) // 2], "p99": 1e3 * ls[min(len(ls) - 1, int(len(ls) * 0.99))], "max": 1e3 * ls[-1], "n": len(ls)}
     if world == 1 and not args.no_cpu_baseline:
-        import mm2oracle as mo
         ns = min(n_reads, args.cpu_sample)
-        o = mo.Oracle(names=names, seqs=[ref.tobytes()])
-        o.set_opt("flag", 4 if args.cigar else 0)
+        t0 = time.perf_counter()
+        o = make_oracle(args, ref, coff, names, preset)
+        t_idx = time.perf_counter() - t0
         cores = os.cpu_count() or 1
         t0 = time.perf_counter()
         ores = o.map_batch(buf[:int(offs[ns])], offs[:ns + 1], cores)
         dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+        out["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port", "index_build_s": t_idx,
                                "sample": "first %d reads (%.1f Mbases) of the same workload, oracle on all host threads" % (ns, int(offs[ns]) / 1e6)}
-        same = bool(np.array_equal(ores.hits["rs"], res.hits["rs"][:len(ores.hits)]) and np.array_equal(ores.hits["mapq"], res.hits["mapq"][:len(ores.hits)]))
-        out["cpu_baseline"]["sample_matches_gpu"] = same
+        if args.workload != "prefix":
+            same = bool(np.array_equal(ores.hits["rs"], res0.hits["rs"][:len(ores.hits)]) and np.array_equal(ores.hits["mapq"], res0.hits["mapq"][:len(ores.hits)]))
+            out["cpu_baseline"]["sample_matches_gpu"] = same
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -236,11 +327,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=200000)
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default 200000; prefix workload 2000000 / 100 batches of 20000)")
+    ap.add_argument("--workload", default="config1", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref", default="", choices=["", "human"], help="prefix/hifi workloads: use the 3.1 Gb reference instead of the 5 Mb one")
+    ap.add_argument("--ref-bases", type=int, default=3_100_000_000)
+    ap.add_argument("--batch", type=int, default=20000, help="prefix workload: reads per streamed batch")
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cigar", action="store_true", help="MM_F_CIGAR on (what mappy-rs itself always runs); default is configs[1] mapping-only")
     args = ap.parse_args()
+    if args.reads <= 0:
+        args.reads = {"config1": 200000, "human": 250000, "prefix": 400000, "hifi": 40000}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -134,6 +134,11 @@ int mmg_index_open(const char *path, const mmg_idxopt_t *io, int n_threads, mmg_
 /* index built from in-memory sequences (benchmark harness; mm_idx_str upstream) */
 int mmg_index_build(const mmg_idxopt_t *io, int n_seq, const char *const *names, const char *const *seqs,
                     const uint32_t *lens, int n_threads, mmg_index **out);
+/* the same, constructed on CUDA device `device` (index_dev.cu) where a device is present and k is odd: the index
+ * then stays resident on that device and mmg_aligner_create() on it uses it in place.  mmg_index_open() on a
+ * FASTA and mmg_index_build() use device 0.  (mm_idx_gen upstream; `Aligner("ref.fa")`, src/lib.rs:395-410) */
+int mmg_index_build_on(const mmg_idxopt_t *io, int n_seq, const char *const *names, const char *const *seqs,
+                       const uint32_t *lens, int n_threads, int device, mmg_index **out);
 int mmg_index_dump(const mmg_index *idx, const char *path);     /* mm_idx_dump (fn_idx_out, src/lib.rs:391) */
 void mmg_index_destroy(mmg_index *idx);
 /* replaces direct reads of mm_idx_t.{k,w,b,flag,n_seq}   src/lib.rs:445,658,663,669,711 */
@@ -208,6 +213,9 @@ double mmg_last_run_ms(const mmg_aligner *al);
  * (x,y), 3 chains u[]; per-read offsets in `off` (n_reads+1). Returns count. */
 int64_t mmg_debug_dump(mmg_aligner *al, mmg_batch *b, int which, uint64_t *x, uint64_t *y, uint64_t cap, uint64_t *off);
 
+/* measurement hook: INT32 lane-operations per second (Gop/s) of dependent IADD3/LOP3 chains on `device`, the
+ * denominator of the integer-issue rooflines (not in MEASURED_PEAKS.json) */
+int mmg_debug_int32_peak(int device, double *gops);
 /* test hook: the device logf used by the mapq computation, over an array */
 int mmg_debug_logf(const float *x, float *y, uint64_t n);
 

@@ -118,6 +118,8 @@ int mmg_host_sketch(const char *seq, int len, int w, int k, uint32_t rid, std::v
 
 const uint64_t *mmg_index_lookup(const mmg_index *idx, uint64_t minier, int *n)
 {
+	*n = 0;
+	if (mmg_index_ensure_host(const_cast<mmg_index*>(idx))) return 0;
 	uint64_t m = ((uint64_t)1 << idx->hbits) - 1, s = mmg_hash_slot(minier, idx->hbits);
 	*n = 0;
 	for (;; s = (s + 1) & m) {
@@ -151,6 +153,15 @@ static inline void table_put(mmg_index *idx, uint64_t minier, int single, uint64
 int32_t mmg_index_cal_max_occ(const mmg_index *idx, float f)
 { /* index.c: mm_idx_cal_max_occ -- ((1-f) n)-th smallest occurrence count + 1 */
 	if (f <= 0.f) return INT32_MAX;
+	if (!idx->occ_hist.empty()) { /* device build: the same order statistic from the occurrence histogram */
+		if (idx->n_keys == 0) return INT32_MAX;
+		uint64_t kk = (uint32_t)((1. - f) * idx->n_keys), acc = 0;
+		for (size_t c = 0; c < idx->occ_hist.size(); ++c) {
+			acc += idx->occ_hist[c];
+			if (acc > kk) return (int32_t)(c + 1);
+		}
+		return (int32_t)(idx->occ_big[kk - acc] + 1);
+	}
 	std::vector<uint32_t> a;
 	a.reserve(idx->n_keys);
 	for (size_t s = 0; s < idx->hkeys.size(); ++s)
@@ -163,9 +174,15 @@ int32_t mmg_index_cal_max_occ(const mmg_index *idx, float f)
 
 struct MzRec { uint64_t m, y; };
 
-static mmg_index *build_from_seqs(int w, int k, int b, int flag, int n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens, int n_threads)
+static mmg_index *build_from_seqs(int w, int k, int b, int flag, int n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens, int n_threads, int device = 0)
 {
 	if (flag & MMG_I_HPC) { mmg_set_error("homopolymer-compressed indexes (MM_I_HPC, map-pb) are outside the supported path"); return 0; }
+	if (!getenv("MMG_HOST_INDEX_BUILD")) { /* device construction whenever a device and the configuration allow it */
+		mmg_index *didx = 0;
+		int rc = mmg_index_build_device(w < 1 ? 1 : w, k, b, flag, n_seq, names, seqs, lens, device, &didx);
+		if (rc == MMG_OK) return didx;
+		if (rc != MMG_EUNSUP) return 0;
+	}
 	mmg_index *idx = new mmg_index();
 	idx->k = k, idx->w = w < 1 ? 1 : w, idx->b = b, idx->flag = flag, idx->n_seq = n_seq;
 	idx->offs.assign(n_seq + 1, 0);
@@ -345,7 +362,13 @@ int mmg_index_build(const mmg_idxopt_t *io, int n_seq, const char *const *names,
 	return *out ? MMG_OK : MMG_EUNSUP;
 }
 
-void mmg_index_destroy(mmg_index *idx) { delete idx; }
+int mmg_index_build_on(const mmg_idxopt_t *io, int n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens, int n_threads, int device, mmg_index **out)
+{
+	*out = build_from_seqs(io->w, io->k, io->bucket_bits, io->flag, n_seq, names, seqs, lens, n_threads, device);
+	return *out ? MMG_OK : MMG_EUNSUP;
+}
+
+void mmg_index_destroy(mmg_index *idx) { if (idx) { mmg_index_free_device(idx); delete idx; } }
 
 int mmg_index_info(const mmg_index *idx, int32_t o[5])
 {
@@ -376,6 +399,7 @@ int mmg_index_getseq(const mmg_index *idx, uint32_t rid, uint32_t st, uint32_t e
 uint64_t mmg_index_entries(const mmg_index *idx, uint64_t *minier, uint64_t *pos, uint64_t cap)
 {
 	uint64_t n = 0;
+	if (mmg_index_ensure_host(const_cast<mmg_index*>(idx))) return 0;
 	for (size_t s = 0; s < idx->hkeys.size(); ++s) {
 		uint64_t key = idx->hkeys[s];
 		if (key == MMG_EMPTY_KEY) continue;
@@ -395,6 +419,8 @@ uint64_t mmg_index_entries(const mmg_index *idx, uint64_t *minier, uint64_t *pos
 
 int mmg_index_dump(const mmg_index *idx, const char *path)
 { /* index.c: mm_idx_dump -- .mmi v2; hash entries go out in key order per bucket */
+	int rc0 = mmg_index_ensure_host(const_cast<mmg_index*>(idx));
+	if (rc0) return rc0;
 	FILE *fp = fopen(path, "wb");
 	if (!fp) { mmg_set_error("cannot write '%s'", path); return MMG_EIO; }
 	uint32_t x[5] = { (uint32_t)idx->w, (uint32_t)idx->k, (uint32_t)idx->b, idx->n_seq, (uint32_t)idx->flag };

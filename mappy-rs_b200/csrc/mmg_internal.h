@@ -31,6 +31,18 @@ struct mmg_index {
 	std::vector<uint64_t> hkeys, hvals;
 	std::vector<uint64_t> pos;
 	uint64_t n_keys;
+	/* An index built on the device (index_dev.cu) stays resident there: dev_* are the uploaded layout on
+	 * device dev_device (-1 = none); the host vectors hkeys/hvals/pos are filled on demand (host_tables). */
+	int dev_device;
+	void *dev_htab; uint64_t *dev_pos; uint32_t *dev_S; uint64_t *dev_seq_off; uint32_t *dev_seq_len;
+	uint64_t n_pos;
+	bool host_tables;
+	/* occurrence histogram taken by the device build (mm_idx_cal_max_occ): occ_hist[c] keys occur c times
+	 * (c < 65536), occ_big = the sorted counts above that */
+	std::vector<unsigned long long> occ_hist;
+	std::vector<uint32_t> occ_big;
+	mmg_index() : k(0), w(0), b(0), flag(0), n_seq(0), hbits(0), n_keys(0), dev_device(-1), dev_htab(0), dev_pos(0), dev_S(0),
+	              dev_seq_off(0), dev_seq_len(0), n_pos(0), host_tables(true) {}
 };
 
 static inline uint64_t mmg_hash_slot(uint64_t minier, uint32_t hbits)
@@ -43,5 +55,10 @@ int mmg_host_sketch(const char *seq, int len, int w, int k, uint32_t rid, std::v
 const uint64_t *mmg_index_lookup(const mmg_index *idx, uint64_t minier, int *n);
 int32_t mmg_index_cal_max_occ(const mmg_index *idx, float f);
 void mmg_set_error(const char *fmt, ...);
+/* index_dev.cu */
+int mmg_index_build_device(int w, int k, int b, int flag, int n_seq, const char *const *names, const char *const *seqs, const uint32_t *lens,
+                           int device, mmg_index **out);
+int mmg_index_ensure_host(mmg_index *idx);
+void mmg_index_free_device(mmg_index *idx);
 
 #endif

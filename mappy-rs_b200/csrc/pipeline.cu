@@ -103,6 +103,11 @@ static int upload_index(mmg_aligner *al)
 	const mmg_index *idx = al->idx;
 	DevIndex &di = al->di;
 	di.k = idx->k, di.w = idx->w, di.b = idx->b, di.flag = idx->flag, di.n_seq = idx->n_seq, di.hbits = idx->hbits;
+	if (idx->dev_device == al->device && idx->dev_htab) { /* built on this device (index_dev.cu): used in place */
+		di.htab = (const mmg_u128*)idx->dev_htab, di.pos = idx->dev_pos, di.S = idx->dev_S, di.seq_off = idx->dev_seq_off, di.seq_len = idx->dev_seq_len;
+		return MMG_OK;
+	}
+	{ int rc0 = mmg_index_ensure_host(const_cast<mmg_index*>(idx)); if (rc0) return rc0; }
 	size_t nslots = idx->hkeys.size();
 	std::vector<mmg_u128> tab(nslots);
 	for (size_t i = 0; i < nslots; ++i) tab[i].x = idx->hkeys[i], tab[i].y = idx->hvals[i];

@@ -54,7 +54,7 @@ HIT_DTYPE = np.dtype([
 STAT_NAMES = ["n_bases", "n_mz", "n_seed", "n_hit", "n_anchor", "n_iter", "n_kept", "n_cell", "n_regs", "n_rechain"]
 N_STAGES = 12
 
-EXPORTS = ["mmg_set_opt", "mmg_mapopt_update", "mmg_index_open", "mmg_index_build", "mmg_index_dump", "mmg_index_destroy",
+EXPORTS = ["mmg_set_opt", "mmg_mapopt_update", "mmg_index_open", "mmg_index_build", "mmg_index_build_on", "mmg_debug_int32_peak", "mmg_index_dump", "mmg_index_destroy",
            "mmg_index_info", "mmg_index_seq_name", "mmg_index_seq_len", "mmg_index_name2id", "mmg_index_getseq",
            "mmg_index_entries", "mmg_aligner_create", "mmg_aligner_destroy", "mmg_aligner_set", "mmg_map_batch",
            "mmg_batch_upload", "mmg_batch_run", "mmg_batch_fetch", "mmg_batch_n_reads", "mmg_batch_n_hits",
@@ -82,6 +82,8 @@ class Lib:
         L.mmg_mapopt_update.argtypes = [P(MapOpt), c_vp]
         L.mmg_index_open.argtypes = [c_cp, P(IdxOpt), c_int, P(c_vp)]
         L.mmg_index_build.argtypes = [P(IdxOpt), c_int, c_vp, c_vp, c_vp, c_int, P(c_vp)]
+        L.mmg_index_build_on.argtypes = [P(IdxOpt), c_int, c_vp, c_vp, c_vp, c_int, c_int, P(c_vp)]
+        L.mmg_debug_int32_peak.argtypes = [c_int, P(ctypes.c_double)]
         L.mmg_index_dump.argtypes = [c_vp, c_cp]
         L.mmg_index_destroy.argtypes = [c_vp]
         L.mmg_index_info.argtypes = [c_vp, c_vp]
@@ -147,14 +149,14 @@ class Index:
         return cls(lib, h)
 
     @classmethod
-    def build(cls, lib, io, names, seqs, n_threads=8):
+    def build(cls, lib, io, names, seqs, n_threads=8, device=0):
         n = len(names)
         keep = [s if isinstance(s, bytes) else (s.tobytes() if hasattr(s, "tobytes") else s.encode()) for s in seqs]
         nm = (ctypes.c_char_p * n)(*[x.encode() for x in names])
         sq = (ctypes.c_char_p * n)(*keep)
         ln = np.array([len(s) for s in keep], dtype=np.uint32)
         h = c_vp()
-        lib.check(lib.L.mmg_index_build(ctypes.byref(io), n, nm, sq, ln.ctypes.data, n_threads, ctypes.byref(h)))
+        lib.check(lib.L.mmg_index_build_on(ctypes.byref(io), n, nm, sq, ln.ctypes.data, n_threads, device, ctypes.byref(h)))
         return cls(lib, h)
 
     def close(self):
@@ -238,6 +240,12 @@ class DeviceAligner:
     def free(self, b): self.lib.L.mmg_batch_destroy(b)
 
     def last_run_ms(self): return float(self.lib.L.mmg_last_run_ms(self.h))
+
+    def int32_peak(self, device=0):
+        """Measured INT32 issue peak (Gop/s) of the device: the denominator of the integer rooflines."""
+        v = ctypes.c_double(0)
+        self.lib.check(self.lib.L.mmg_debug_int32_peak(device, ctypes.byref(v)))
+        return float(v.value)
 
     def stage_times(self):
         ms = np.zeros(N_STAGES, dtype=np.float64); ln = np.zeros(N_STAGES, dtype=np.uint64)

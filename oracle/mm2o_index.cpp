@@ -15,6 +15,8 @@
 #include <algorithm>
 #include "mm2o.h"
 #include "mm2o_sort.h"
+#include <thread>
+#include <atomic>
 
 #define MM_IDX_MAGIC "MMI\2"
 
@@ -149,13 +151,48 @@ mm_idx_t *mm_idx_build(int w, int k, int b, int flag, int n_seq, const char **na
 	}
 	std::vector<mm128_v> A((size_t)1 << b);
 	int mask = (1 << b) - 1;
+	/* The contigs are sketched and the buckets post-processed by a few threads (upstream: kt_pipeline /
+	 * kt_for); the index does not depend on the order in which minimizers reach a bucket, because every
+	 * position run is sorted in bucket_post. */
+	int n_thr = (int)std::thread::hardware_concurrency();
+	if (n_thr < 1) n_thr = 1;
+	if (n_thr > 32) n_thr = 32;
+	if (sum_len < 50000000) n_thr = 1;
+	std::vector<mm128_v> per(n_seq);
+	{
+		std::atomic<int> next(0);
+		auto work = [&]() {
+			for (;;) {
+				int i = next.fetch_add(1);
+				if (i >= n_seq) break;
+				if (lens[i] > 0) mm_sketch(seqs[i], lens[i], mi->w, mi->k, i, flag & MM_I_HPC, &per[i]);
+			}
+		};
+		std::vector<std::thread> th;
+		for (int t = 1; t < n_thr && t < n_seq; ++t) th.emplace_back(work);
+		work();
+		for (auto &t : th) t.join();
+	}
 	for (int i = 0; i < n_seq; ++i) {
-		mm128_v a;
-		if (lens[i] > 0) mm_sketch(seqs[i], lens[i], mi->w, mi->k, i, flag & MM_I_HPC, &a);
+		const mm128_v &a = per[i];
 		for (size_t j = 0; j < a.size(); ++j) // index.c: mm_idx_add
 			A[a[j].x >> 8 & mask].push_back(a[j]);
+		mm128_v().swap(per[i]);
 	}
-	for (size_t i = 0; i < A.size(); ++i) bucket_post(mi, &mi->B[i], A[i]);
+	{
+		std::atomic<size_t> next(0);
+		auto work = [&]() {
+			for (;;) {
+				size_t i = next.fetch_add(64);
+				if (i >= A.size()) break;
+				for (size_t q = i; q < i + 64 && q < A.size(); ++q) { bucket_post(mi, &mi->B[q], A[q]); mm128_v().swap(A[q]); }
+			}
+		};
+		std::vector<std::thread> th;
+		for (int t = 1; t < n_thr; ++t) th.emplace_back(work);
+		work();
+		for (auto &t : th) t.join();
+	}
 	return mi;
 }
 

@@ -17,6 +17,7 @@ struct emu_event_st { std::chrono::steady_clock::time_point t; };
 static const char *emu_err = "no error";
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { memset(p, 0, sizeof(*p)); const char *e = getenv("MMG_EMU_SMS"); p->multiProcessorCount = e ? atoi(e) : 4; p->totalGlobalMem = (size_t)8 << 30; p->sharedMemPerBlockOptin = 227 * 1024; strcpy(p->name, "mmg-emu"); p->major = 10; return cudaSuccess; }
 cudaError_t cudaMalloc(void **p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }

@@ -46,6 +46,7 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
 cudaError_t cudaGetDeviceCount(int *n);
 cudaError_t cudaSetDevice(int d);
+cudaError_t cudaGetDevice(int *d);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d);
 cudaError_t cudaMalloc(void **p, size_t n);
 cudaError_t cudaFree(void *p);
