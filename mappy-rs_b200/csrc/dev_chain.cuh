@@ -50,23 +50,48 @@ static __device__ void dev_backtrack_compact(int n, uint64_t *ax, uint64_t *ay, 
 	}
 	__syncwarp();
 	if (n_z > 0) {
-		if (lane == 0) {
-			dev_radix_sort_128x(zx, zy, n_z, bkt, (int*)v); /* v[] is the sort's range stack; it is free again below */
-			for (int k = n_z - 1; k >= 0; --k) {
-				int zi = (int)zy[k];
-				if (t[zi] == 0) {
-					int n_v0 = n_v, i;
-					int32_t zkx = (int32_t)zx[k], sc;
-					int end_i = dev_chain_bk_end(max_drop, zkx, zi, f, p, t);
-					for (i = zi; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
-					sc = i < 0 ? zkx : zkx - f[i];
-					if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint32_t)(n_v - n_v0);
-					else n_v = n_v0;
+		dev_radix_sort_warp(zx, zy, n_z, bkt, (int*)v); /* v[] is the sort's range stack; it is free again below */
+		/* mg_chain_backtrack: chain ends in descending score order.  32 candidates are tested per step; an
+		 * end whose anchor is still unused starts a walk.  mg_chain_bk_end's three passes over the chain
+		 * (mark, unmark, collect) are one walk here: the path goes to v[] as it is followed, the position of
+		 * the best prefix is tracked, and only that prefix is then marked used (by all lanes). */
+		for (int kb = n_z - 1; kb >= 0; kb -= 32) {
+			const int k = kb - lane;
+			const int zi = k >= 0 ? (int)zy[k] : -1;
+			const int32_t zkx = k >= 0 ? (int32_t)zx[k] : 0;
+			int first = 0; /* lanes below `first` are done */
+			for (;;) {
+				const bool cand = k >= 0 && lane >= first && t[zi] == 0;
+				const uint32_t cm = __ballot_sync(MMG_FULL, cand);
+				if (!cm) break;
+				const int src = __ffs((int)cm) - 1;
+				first = src + 1;
+				const int czi = __shfl_sync(MMG_FULL, zi, src);
+				const int32_t czkx = __shfl_sync(MMG_FULL, zkx, src);
+				int best_len = 0;
+				int32_t max_s = 0;
+				if (lane == 0) {
+					int m = 0, cur = czi;
+					do {
+						v[n_v + m] = cur, ++m;
+						const int nxt = p[cur];
+						const int32_t sc1 = nxt < 0 ? czkx : czkx - f[nxt];
+						cur = nxt;
+						if (sc1 > max_s) max_s = sc1, best_len = m;
+						else if (max_s - sc1 > max_drop) break;
+					} while (cur >= 0 && t[cur] == 0);
 				}
+				best_len = __shfl_sync(MMG_FULL, best_len, 0);
+				max_s = __shfl_sync(MMG_FULL, max_s, 0);
+				__syncwarp();
+				for (int j = lane; j < best_len; j += 32) t[v[n_v + j]] = 1;
+				if (max_s >= min_sc && best_len > 0 && best_len >= min_cnt) {
+					if (lane == 0) u[n_u] = (uint64_t)max_s << 32 | (uint32_t)best_len;
+					++n_u, n_v += best_len;
+				}
+				__syncwarp();
 			}
 		}
-		n_u = __shfl_sync(MMG_FULL, n_u, 0);
-		n_v = __shfl_sync(MMG_FULL, n_v, 0);
 	}
 	__syncwarp();
 	if (n_u > 0) {

@@ -100,6 +100,104 @@ static __device__ void dev_radix_sort_t(uint64_t *x, YT *y, int n, int *bkt, int
 	}
 }
 
+/* The same sort called by a WHOLE WARP (all 32 lanes, converged): the counting loops, the bucket prefix sums and
+ * the insertion sorts of the leaf ranges (one leaf per lane) run in parallel; only the cycle-leader permutation of
+ * a pass, which has no parallel form, stays on lane 0.  Ranges are disjoint, so the order in which they are
+ * processed does not change the result.  bkt must be shared memory (atomics), 512 ints. */
+template<typename YT>
+static __device__ void dev_radix_sort_warp(uint64_t *x, YT *y, int n, int *bkt, int *stk)
+{
+	const int lane = mmg_lane();
+	const uint32_t lt = mmg_lanemask_lt();
+	if (n <= 64) {
+		if (lane == 0) dev_insertsort_t(x, y, 0, n);
+		__syncwarp();
+		return;
+	}
+	int *bb = bkt, *be = bkt + 256;
+	uint64_t diff = 0;
+	{
+		const uint64_t x0 = x[0];
+		for (int i = 1 + lane; i < n; i += 32) diff |= x[i] ^ x0;
+		const uint32_t lo = __reduce_or_sync(MMG_FULL, (uint32_t)diff), hi = __reduce_or_sync(MMG_FULL, (uint32_t)(diff >> 32));
+		diff = (uint64_t)hi << 32 | lo;
+	}
+	if (diff == 0) return;
+	const int s0 = ((63 - __clzll((long long)diff)) >> 3) << 3;
+	for (int k = lane; k < 256; k += 32) be[k] = 0;
+	if (lane == 0) stk[0] = 0, stk[1] = n, stk[2] = s0;
+	int sp = 1;
+	__syncwarp();
+	while (sp > 0) {
+		--sp;
+		const int beg = stk[3 * sp], end = stk[3 * sp + 1];
+		int s = stk[3 * sp + 2];
+		int kmin, kmax;
+		for (;;) { /* be[] is all zero here */
+			int mn = 255, mx = 0;
+			for (int i = beg + lane; i < end; i += 32) {
+				int b = (int)((x[i] >> s) & 255);
+				atomicAdd(&be[b], 1);
+				mn = b < mn ? b : mn, mx = b > mx ? b : mx;
+			}
+			kmin = __reduce_min_sync(MMG_FULL, mn), kmax = __reduce_max_sync(MMG_FULL, mx);
+			__syncwarp();
+			if (kmin != kmax || s == 0) break;
+			if (lane == 0) be[kmin] = 0;    /* one bucket holds the whole range: nothing moves, next byte */
+			__syncwarp();
+			s -= 8;
+		}
+		{
+			int carry = beg;
+			for (int k0 = kmin; k0 <= kmax; k0 += 32) {
+				const int k = k0 + lane, cnt = k <= kmax ? be[k] : 0;
+				int tot, ex = mmg_warp_excl_scan(cnt, &tot);
+				if (k <= kmax) bb[k] = carry + ex, be[k] = carry + ex + cnt;
+				carry += tot;
+			}
+		}
+		__syncwarp();
+		if (lane == 0) {
+			for (int k = kmin; k <= kmax;) {
+				if (bb[k] != be[k]) {
+					int l = (int)((x[bb[k]] >> s) & 255);
+					if (l != k) {
+						uint64_t tx = x[bb[k]];
+						YT ty = y[bb[k]];
+						do {
+							uint64_t sx = tx;
+							YT sy = ty;
+							int q = bb[l]++;
+							tx = x[q], ty = y[q];
+							x[q] = sx, y[q] = sy;
+							l = (int)((tx >> s) & 255);
+						} while (l != k);
+						x[bb[k]] = tx, y[bb[k]] = ty;
+						++bb[k];
+					} else ++bb[k];
+				} else ++k;
+			}
+		}
+		__syncwarp();
+		if (s) {
+			const int s2 = s > 8 ? s - 8 : 0;
+			for (int k0 = kmin; k0 <= kmax; k0 += 32) {
+				const int k = k0 + lane;
+				int start = 0, e = 0, sz = 0;
+				if (k <= kmax) e = be[k], start = k == kmin ? beg : be[k - 1], sz = e - start;
+				const bool push = sz > 64;
+				const uint32_t pm = __ballot_sync(MMG_FULL, push);
+				if (push) { const int q = sp + __popc(pm & lt); stk[3 * q] = start, stk[3 * q + 1] = e, stk[3 * q + 2] = s2; }
+				sp += __popc(pm);
+				if (sz > 1 && sz <= 64) dev_insertsort_t(x, y, start, e);
+			}
+		}
+		__syncwarp();
+		for (int k = kmin + lane; k <= kmax; k += 32) be[k] = 0;
+		__syncwarp();
+	}
+}
+
 static __device__ void dev_radix_sort_128x(uint64_t *x, uint64_t *y, int n, int *bkt, int *stk)
 {
 	dev_radix_sort_t<uint64_t, true>(x, y, n, bkt, stk);
