@@ -190,6 +190,8 @@ def run_ours(args, rank, local_rank, world):
     lib.check(lib.L.mmg_mapopt_update(ctypes.byref(mopt), idx.h))
     al = _mmg.DeviceAligner(lib, idx, mopt, device=local_rank)
     al.set("profile", 1)
+    if os.environ.get("MMG_SORT_SMALL_MAX"):
+        al.set("sort_small_max", int(os.environ["MMG_SORT_SMALL_MAX"]))
     # pinned host staging (torch is plumbing here: pinned memory + process group)
     hbuf = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
     hbuf.numpy()[:] = buf

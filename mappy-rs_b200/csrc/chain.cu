@@ -85,6 +85,27 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 		uint64_t mii_x = 0;
 		int32_t mii_f = 0;
 		for (int i = 0; i < n; ++i) {
+			{ /* Anchors without any predecessor in range (the previous anchor is on another strand/contig or
+			   * more than max_dist_x behind - most index hits on a large reference) are settled 32 at a time:
+			   * f = span, p = -1, and the loop state afterwards is what the scalar path leaves: st at the
+			   * anchor itself, and the anchor as the `max_ii` candidate. */
+				const int j = i + lane;
+				uint64_t xj = 0, xp = 0;
+				if (j < n) { xj = ax[j]; if (j > 0) xp = ax[j - 1]; }
+				const bool iso = j < n && (j == 0 || (xp >> 32) != (xj >> 32) || xj > xp + (uint64_t)max_dist_x);
+				const uint32_t im = __ballot_sync(MMG_FULL, iso);
+				const int run = im == MMG_FULL ? 32 : __ffs((int)~im) - 1;
+				if (run > 0) {
+					int32_t sp = 0;
+					if (lane < run) { sp = (int32_t)(ay[j] >> 32 & 0xff); f[j] = sp, p[j] = -1, t[j] = 0; }
+					const int last = run - 1;
+					st = i + last, max_ii = i + last;
+					mii_x = __shfl_sync(MMG_FULL, xj, last), mii_f = __shfl_sync(MMG_FULL, sp, last);
+					i += last;
+					__syncwarp();
+					continue;
+				}
+			}
 			const uint64_t aix = ax[i], aiy = ay[i];
 			/* advance st: first j that shares the target strand and is within max_dist_x */
 			for (;;) {

@@ -201,6 +201,7 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	const int64_t unsup = 0x80LL | 0x100LL | 0x200LL | 0x1000LL | 0x2000LL | MMG_F_FOR_ONLY | MMG_F_REV_ONLY | 0x400000LL | 0x20000000LL | MMG_F_RMQ | 0x100000000LL | 0x1LL | 0x2LL;
 	if (mo->flag & unsup) { mmg_set_error("mapping flag 0x%llx selects a code path outside the supported long-read path", (unsigned long long)(mo->flag & unsup)); return MMG_EUNSUP; }
 	if (idx->flag & MMG_I_HPC) { mmg_set_error("homopolymer-compressed indexes are not supported"); return MMG_EUNSUP; }
+	if (idx->offs.back() >= ((uint64_t)1 << 35)) { mmg_set_error("references of 2^35 bases or more are not supported"); return MMG_EUNSUP; }
 	CK(cudaSetDevice(device));
 	mmg_aligner *al = new mmg_aligner();
 	al->idx = idx, al->mo = *mo, al->device = device;
@@ -264,6 +265,7 @@ void mmg_aligner_destroy(mmg_aligner *al)
 int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 {
 	if (strcmp(key, "profile") == 0) { al->profile = (int)v; return MMG_OK; }
+	if (strcmp(key, "sort_small_max") == 0) { mmg_sort_set_small_max((int)v); return MMG_OK; }
 	if (al->arenas_ready) { mmg_set_error("arena sizes are fixed after the first batch"); return MMG_EINVAL; }
 	if (strcmp(key, "chunk_bases") == 0) al->cap_bases = (uint64_t)v;
 	else if (strcmp(key, "chunk_reads") == 0) al->cap_reads = (uint32_t)v;
@@ -507,7 +509,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 		}
 		if (wi + 10 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
 		STAGE_BEGIN(); launch_expand(c, al->di, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_EXPAND);
-		STAGE_BEGIN(); launch_sort(c, s0, s1, al->n_sms, st, work + wi); wi += 3; STAGE_END(ST_SORT);
+		STAGE_BEGIN(); launch_sort(c, al->di, s0, s1, al->n_sms, st, work + wi); wi += 3; STAGE_END(ST_SORT);
 		STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
 		STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
 		STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);

@@ -32,7 +32,7 @@ __device__ __forceinline__ bool key_gt(uint64_t xa, uint32_t ia, uint64_t xb, ui
  * do not fit its tile to big_list; the BIG instantiation (LIST = true) takes its reads from there. */
 template<int ELEMS, bool LIST>
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work, uint32_t *big_list, uint32_t *n_big)
+sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work, uint32_t *big_list, uint32_t *n_big, int small_max)
 {
 	MMG_DYN_SMEM(smem_raw);
 	__shared__ uint32_t s_item;
@@ -49,7 +49,7 @@ sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work, uint32_t *big_
 		if (s_item >= n_items) break;
 		const uint32_t r = LIST ? big_list[s_item] : r0 + s_item;
 		const int n = (int)c.n_a[r];
-		if (!LIST && n > ELEMS) { /* uniform over the CTA */
+		if (!LIST && n > small_max) { /* uniform over the CTA */
 			if (tid == 0) big_list[atomicAdd(n_big, 1u)] = r;
 			__syncthreads();
 			continue;
@@ -123,19 +123,158 @@ sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work, uint32_t *big_
 	}
 }
 
-int launch_sort(const ChunkDev &c, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work)
+/* ---- large reads: LSD radix sort of the whole read by one CTA ------------------------------------------
+ * A record is key<<28 | source index, with key = strand:1 | linear target coordinate:35 (seq_off[rid] + pos), which
+ * orders exactly like x = strand<<63 | rid<<32 | pos.  8-bit digits; a pass is a warp-level multi-split: warp w
+ * owns a contiguous slice, __match_any_sync groups the lanes of a step by digit, the group leader bumps the
+ * warp's private counter, and a lane's rank is its position inside the group - stable, no atomics.  Passes whose
+ * digit is the same in every record are skipped.  The records ping-pong in the read's 2n-word global scratch
+ * (L1/L2 resident), so any read length works and shared memory only holds the 8 x 256 counters.
+ * O(n) work per pass instead of the O(n log^2 n) of the bitonic network the small reads use. */
+#define RSORT_WARPS 8
+#define RSORT_IDX_BITS 28
+#define RSORT_IDX_MASK 0x0fffffffULL
+
+__device__ __forceinline__ uint64_t rsort_record(uint64_t x, uint32_t i, const uint64_t *seq_off)
 {
-	/* work[0]: read counter of the small pass, work[1]: length of big_list, work[2]: list counter of the big pass */
-	const size_t smem_big = (size_t)SORT_SMEM_ELEMS * 12, smem_small = (size_t)SORT_SMALL_ELEMS * 12;
-	static bool attr_done = false;
-	if (!attr_done) { cudaFuncSetAttribute(sort_kernel<SORT_SMEM_ELEMS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big); attr_done = true; }
+	const uint64_t lin = seq_off[(uint32_t)(x >> 32) & 0x7fffffffu] + (uint32_t)x;
+	return ((x >> 63) << 35 | lin) << RSORT_IDX_BITS | i;
+}
+
+/* sorts the n keys srcx[] (stable); afterwards A[0..n) holds the records in order.  Returns the buffer holding them. */
+static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64_t *seq_off, uint64_t *A, uint64_t *B, uint32_t *cnt, uint32_t *s_red)
+{
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const uint32_t lt = mmg_lanemask_lt();
+	uint64_t diff = 0;
+	{
+		const uint64_t r0 = rsort_record(srcx[0], 0, seq_off);
+		for (int i = tid; i < n; i += RSORT_WARPS * 32) {
+			const uint64_t rec = rsort_record(srcx[i], (uint32_t)i, seq_off);
+			A[i] = rec;
+			diff |= rec ^ r0;
+		}
+		uint32_t lo = __reduce_or_sync(MMG_FULL, (uint32_t)diff), hi = __reduce_or_sync(MMG_FULL, (uint32_t)(diff >> 32));
+		if (lane == 0) s_red[w] = lo, s_red[RSORT_WARPS + w] = hi;
+		__syncthreads();
+		lo = 0, hi = 0;
+		for (int q = 0; q < RSORT_WARPS; ++q) lo |= s_red[q], hi |= s_red[RSORT_WARPS + q];
+		diff = (uint64_t)hi << 32 | lo;
+		__syncthreads();
+	}
+	const int chunk = ((n + RSORT_WARPS - 1) / RSORT_WARPS + 31) & ~31;
+	const int beg = w * chunk < n ? w * chunk : n, end = beg + chunk < n ? beg + chunk : n;
+	for (int shift = RSORT_IDX_BITS; shift < 64; shift += 8) {
+		if (((diff >> shift) & 0xff) == 0) continue;
+		for (int j = tid; j < RSORT_WARPS * 256; j += RSORT_WARPS * 32) cnt[j] = 0;
+		__syncthreads();
+		for (int b0 = beg; b0 < end; b0 += 32) {
+			const int i = b0 + lane;
+			const bool valid = i < end;
+			const uint32_t d = valid ? (uint32_t)(A[i] >> shift) & 0xffu : 256u;
+			const uint32_t peers = __match_any_sync(MMG_FULL, d);
+			if (valid && (peers & lt) == 0) cnt[w * 256 + d] += (uint32_t)__popc(peers);
+			__syncwarp();
+		}
+		__syncthreads();
+		{ /* exclusive scan in (digit, warp) order: thread t owns digit t */
+			uint32_t loc[RSORT_WARPS], tot = 0;
+			for (int q = 0; q < RSORT_WARPS; ++q) loc[q] = tot, tot += cnt[q * 256 + tid];
+			uint32_t x = tot;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				uint32_t y = __shfl_up_sync(MMG_FULL, x, o);
+				if (lane >= o) x += y;
+			}
+			if (lane == 31) s_red[w] = x;
+			__syncthreads();
+			uint32_t pre = 0;
+			for (int q = 0; q < w; ++q) pre += s_red[q];
+			const uint32_t base = pre + x - tot;
+			for (int q = 0; q < RSORT_WARPS; ++q) cnt[q * 256 + tid] = base + loc[q];
+		}
+		__syncthreads();
+		for (int b0 = beg; b0 < end; b0 += 32) {
+			const int i = b0 + lane;
+			const bool valid = i < end;
+			const uint64_t rec = valid ? A[i] : 0;
+			const uint32_t d = valid ? (uint32_t)(rec >> shift) & 0xffu : 256u;
+			const uint32_t peers = __match_any_sync(MMG_FULL, d);
+			const uint32_t base = valid ? cnt[w * 256 + d] : 0;
+			__syncwarp();
+			if (valid && (peers & lt) == 0) cnt[w * 256 + d] = base + (uint32_t)__popc(peers);
+			if (valid) B[base + (uint32_t)__popc(peers & lt)] = rec;
+			__syncwarp();
+		}
+		__syncthreads();
+		uint64_t *tmp = A; A = B, B = tmp;
+	}
+	return A;
+}
+
+__global__ void __launch_bounds__(RSORT_WARPS * 32)
+radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uint32_t *list, const uint32_t *n_list)
+{
+	__shared__ uint32_t s_item;
+	__shared__ int s_tie;
+	__shared__ int s_bkt[512];
+	__shared__ uint32_t s_cnt[RSORT_WARPS * 256];
+	__shared__ uint32_t s_red[2 * RSORT_WARPS];
+	const int tid = threadIdx.x, nt = blockDim.x;
+	const uint32_t n_items = *n_list;
+	for (;;) {
+		if (tid == 0) s_item = atomicAdd(work, 1u), s_tie = 0;
+		__syncthreads();
+		if (s_item >= n_items) break;
+		const uint32_t r = list[s_item];
+		const int n = (int)c.n_a[r];
+		const uint64_t ab = c.a_off[r] - c.a_off0;
+		const uint64_t *ax = c.ax + ab, *ay = c.ay + ab;
+		uint64_t *bx = c.bx + ab, *by = c.by + ab;
+		uint64_t *zx = c.zx + 2 * ab, *zy = c.zy + 2 * ab;
+		const uint64_t *srcx = ax, *srcy = ay;
+		for (int pass = 0; pass < 2 && n > 1; ++pass) {
+			const uint64_t *S = rsort_read(srcx, n, seq_off, zx, zx + n, s_cnt, s_red);
+			int tie = 0;
+			for (int i = tid; i < n; i += nt) {
+				const uint64_t rec = S[i];
+				const uint32_t j = (uint32_t)(rec & RSORT_IDX_MASK);
+				bx[i] = srcx[j], by[i] = srcy[j];
+				if (i + 1 < n && (S[i + 1] >> RSORT_IDX_BITS) == (rec >> RSORT_IDX_BITS)) tie = 1;
+			}
+			if (pass == 0 && tie && n > 64) s_tie = 1;
+			__syncthreads();
+			if (pass == 1 || !s_tie) break;
+			/* equal keys: replay upstream's unstable radix passes on one thread, then sort again stably
+			 * by (key, position after those passes) - see the tie path of sort_kernel */
+			uint32_t *ki = (uint32_t*)(zx + n);
+			for (int i = tid; i < n; i += nt) zx[i] = ax[i], ki[i] = (uint32_t)i;
+			__syncthreads();
+			if (tid == 0) {
+				dev_radix_sort_t<uint32_t, false>(zx, ki, n, s_bkt, c.f + ab);
+				c.flags[r] |= 1u;
+			}
+			__syncthreads();
+			for (int i = tid; i < n; i += nt) zy[i] = zx[i], zy[n + i] = ay[ki[i]];
+			__syncthreads();
+			srcx = zy, srcy = zy + n;
+		}
+		if (n == 1 && tid == 0) bx[0] = ax[0], by[0] = ay[0];
+		__syncthreads();
+	}
+}
+
+static int g_sort_small_max = 1024;
+void mmg_sort_set_small_max(int v) { g_sort_small_max = v < 0 ? 0 : v > SORT_SMALL_ELEMS ? SORT_SMALL_ELEMS : v; }
+
+int launch_sort(const ChunkDev &c, const DevIndex &di, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work)
+{
+	/* work[0]: read counter of the small pass, work[1]: length of big_list, work[2]: list counter of the radix pass */
+	const size_t smem_small = (size_t)SORT_SMALL_ELEMS * 12;
 	int grid = n_sms * 8, need = (int)(r1 - r0);
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
-	MMG_LAUNCH((sort_kernel<SORT_SMALL_ELEMS, false>), grid, SORT_THREADS, smem_small, st, c, r0, r1, work, c.big_list, work + 1);
-	grid = n_sms * 2;
-	if (grid > need) grid = need;
-	if (grid < 1) grid = 1;
-	MMG_LAUNCH((sort_kernel<SORT_SMEM_ELEMS, true>), grid, SORT_THREADS, smem_big, st, c, r0, r1, work + 2, c.big_list, work + 1);
+	MMG_LAUNCH((sort_kernel<SORT_SMALL_ELEMS, false>), grid, SORT_THREADS, smem_small, st, c, r0, r1, work, c.big_list, work + 1, g_sort_small_max);
+	MMG_LAUNCH(radix_sort_kernel, grid, RSORT_WARPS * 32, 0, st, c, di.seq_off, work + 2, (const uint32_t*)c.big_list, (const uint32_t*)(work + 1));
 	return 0;
 }

@@ -16,7 +16,8 @@ int launch_sketch(const ChunkDev &c, const DevIndex &di, int n_sms, cudaStream_t
 int launch_seed(const ChunkDev &c, const DevIndex &di, const DevOpt &o, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_scan_u32(const uint32_t *in, uint64_t *out, uint32_t n, cudaStream_t st);  /* out[n] = total */
 int launch_expand(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
-int launch_sort(const ChunkDev &c, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_sort(const ChunkDev &c, const DevIndex &di, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+void mmg_sort_set_small_max(int v); /* reads with more anchors take the radix pass (tuning knob "sort_small_max") */
 int launch_chain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_backtrack(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
 #define RMQ_NODE_BYTES 40 /* sizeof(RNode) in rmq.cu; the arena holds 2 * (anchors + reads) nodes */

@@ -151,6 +151,7 @@ static void warp_complete(BlockCtx *b, int w)
 		case EMU_SHFL_DOWN: src = l + ws->args[l]; res[l] = (src < base + width && (part >> src & 1)) ? ws->vals[src] : ws->vals[l]; break;
 		case EMU_SHFL_XOR: src = l ^ ws->args[l]; res[l] = (src < base + width && src >= base && (part >> src & 1)) ? ws->vals[src] : ws->vals[l]; break;
 		case EMU_BALLOT: res[l] = ballot & ws->mask; break;
+		case EMU_MATCH_ANY: { unsigned m = 0; for (int q = 0; q < 32; ++q) if ((part >> q & 1) && ws->vals[q] == ws->vals[l]) m |= 1u << q; res[l] = m; break; }
 		default: res[l] = acc; break;
 		}
 	}

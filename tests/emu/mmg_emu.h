@@ -103,6 +103,7 @@ static inline int __reduce_max_sync(unsigned m, int v) { return (int)(int64_t)em
 static inline int __reduce_min_sync(unsigned m, int v) { return (int)(int64_t)emu_collective(EMU_RED_MIN_S, m, (uint64_t)(int64_t)v, 0, 32); }
 static inline unsigned __reduce_max_sync(unsigned m, unsigned v) { return (unsigned)emu_collective(EMU_RED_MAX_U, m, v, 0, 32); }
 static inline unsigned __reduce_min_sync(unsigned m, unsigned v) { return (unsigned)emu_collective(EMU_RED_MIN_U, m, v, 0, 32); }
+template<typename T> static inline unsigned __match_any_sync(unsigned m, T v) { return (unsigned)emu_collective(EMU_MATCH_ANY, m, emu_to_bits(v), 0, 32); }
 static inline unsigned __activemask(void) { return 0xffffffffu; }
 
 /* ---- scalar intrinsics ---- */

@@ -221,3 +221,21 @@ def test_equal_anchor_keys_replay_upstream_order(emu_lib, oracle_mod):
         assert stage_diffs == [] and parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
     finally:
         c.close()
+
+
+def test_radix_sort_pass_for_every_read(emu_lib, oracle_mod):
+    """sort_small_max = 0 sends every read through the CTA radix sort (the path of reads with > 1024 anchors),
+    including its equal-key replay; two contigs so that the linear target coordinate spans contigs."""
+    ref, coff, names, seqs = parity.random_reference(93, [90000, 50000])
+    c = parity.Case(emu_lib, names, seqs)
+    try:
+        c.aligner.set("sort_small_max", 0)
+        b1, o1 = oracle_mod.pack_reads(_dup_reads(ref[:90000], 10, 94))
+        b2, o2, _ = data_gen.make_reads(95, ref, coff, 60, 200, 6000)
+        buf = np.concatenate([b1, b2]); offs = np.concatenate([o1, o2[1:] + o1[-1]])
+        dev, stage_diffs = parity.compare_stages(c, buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert stage_diffs == [] and parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
+    finally:
+        c.aligner.set("sort_small_max", 1024)
+        c.close()
