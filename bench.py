@@ -260,9 +260,10 @@ def run_ours(args, rank, local_rank, world):
         d2h = 0
         for v, o in views:
             t1 = time.perf_counter()
-            r = al.map_batch(v, o)
+            r = al.map_batch(v, o, zero_copy=True)   # results are read in place (views of the library's host memory)
             lat.append(time.perf_counter() - t1)
             d2h += r.hits.nbytes + r.cigar.nbytes + (len(o) - 1) * 4 + 80
+            r.close()
     barrier()
     e2e_s = maxrank((time.perf_counter() - t0) / args.steps)
     sampler.stop_flag = True

@@ -172,7 +172,7 @@ table_fill_kernel(const uint64_t *key, const uint64_t *val, const uint64_t *head
 		cnt = head_pos[h + 1] - i;
 		const uint64_t kv = cnt == 1 ? (k << 1 | 1ULL) : (k << 1), vv = cnt == 1 ? val[i] : (head_off[h] << 32 | cnt);
 		const uint64_t m = ((uint64_t)1 << hbits) - 1;
-		uint64_t s = (k * 0x9E3779B97F4A7C15ULL) >> (64 - hbits);
+		uint64_t s = ((k * 0x9E3779B97F4A7C15ULL) >> (64 - hbits)) & ~(uint64_t)1;
 		for (;; s = (s + 1) & m) {
 			unsigned long long old = atomicCAS((unsigned long long*)&tab[s].x, (unsigned long long)MMG_EMPTY_KEY, (unsigned long long)kv);
 			if (old == (unsigned long long)MMG_EMPTY_KEY) { tab[s].y = vv; break; }
@@ -398,7 +398,7 @@ int mmg_index_build_device(int w, int k, int b, int flag, int n_seq, const char 
 	/* table */
 	{
 		uint32_t hb = 4;
-		while (((uint64_t)1 << hb) < n_keys * 2) ++hb;
+		while (((uint64_t)1 << hb) < n_keys * 4) ++hb;
 		idx->hbits = hb, idx->n_keys = n_keys, idx->n_pos = n_multi;
 		const uint64_t nslots = (uint64_t)1 << hb;
 		const uint32_t big_cap = 1u << 16;

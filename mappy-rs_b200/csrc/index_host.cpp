@@ -136,7 +136,7 @@ const uint64_t *mmg_index_lookup(const mmg_index *idx, uint64_t minier, int *n)
 static void table_alloc(mmg_index *idx, uint64_t n_keys)
 {
 	uint32_t hb = 4;
-	while (((uint64_t)1 << hb) < n_keys * 2) ++hb;
+	while (((uint64_t)1 << hb) < n_keys * 4) ++hb;
 	idx->hbits = hb, idx->n_keys = n_keys;
 	idx->hkeys.assign((size_t)1 << hb, MMG_EMPTY_KEY);
 	idx->hvals.assign((size_t)1 << hb, 0);

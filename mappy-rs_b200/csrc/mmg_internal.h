@@ -15,7 +15,8 @@
  *
  * Upstream keeps 2^b khash tables (index.c: mm_idx_bucket_t); a GPU lookup wants
  * one probe = one 16-byte load, so the buckets are flattened into a single
- * open-addressing table (linear probing, load factor <= 0.5):
+ * open-addressing table (linear probing from an even slot, load factor <= 0.25, so that a lookup reads the
+ * two slots of one 32-byte sector per round trip and almost always ends after the first):
  *   slot.key = minimizer<<1 | is_single   (MMG_EMPTY_KEY when free)
  *   slot.val = position word y            (is_single)
  *            = offset<<32 | count into pos[]  (otherwise; runs sorted ascending)
@@ -47,7 +48,7 @@ struct mmg_index {
 
 static inline uint64_t mmg_hash_slot(uint64_t minier, uint32_t hbits)
 {
-	return (minier * 0x9E3779B97F4A7C15ULL) >> (64 - hbits);
+	return ((minier * 0x9E3779B97F4A7C15ULL) >> (64 - hbits)) & ~(uint64_t)1; /* probing starts at an even slot */
 }
 
 /* index_host.cpp */

@@ -20,19 +20,26 @@
 #define SEED_NCNT 1024          /* query-occurrence counters per warp */
 #define MAX_MAX_HIGH_OCC 128    /* seed.c */
 
+/* index.c mm_idx_get on the flat table: linear probing that starts at an even slot and reads the slot pair of
+ * one 32-byte sector per round trip (load factor <= 0.25: a miss - most minimizers of a noisy read - almost
+ * always ends at the first pair) */
 __device__ __forceinline__ bool dev_idx_get(const DevIndex &di, uint64_t minier, uint32_t *n, uint64_t *val)
 {
 	const uint64_t m = ((uint64_t)1 << di.hbits) - 1;
-	uint64_t s = (minier * 0x9E3779B97F4A7C15ULL) >> (64 - di.hbits);
+	uint64_t s = ((minier * 0x9E3779B97F4A7C15ULL) >> (64 - di.hbits)) & ~(uint64_t)1;
 	for (;;) {
-		mmg_u128 e = di.htab[s];
-		if (e.x == MMG_INF64) return false;
-		if (e.x >> 1 == minier) {
-			if (e.x & 1) *n = 1, *val = e.y;          /* the value is the position word itself */
-			else *n = (uint32_t)e.y, *val = e.y >> 32; /* offset into pos[] */
-			return true;
+		const mmg_u128 e0 = di.htab[s], e1 = di.htab[s + 1];
+		mmg_u128 e;
+		if (e0.x == MMG_INF64) return false;
+		if (e0.x >> 1 == minier) e = e0;
+		else {
+			if (e1.x == MMG_INF64) return false;
+			if (e1.x >> 1 != minier) { s = (s + 2) & m; continue; }
+			e = e1;
 		}
-		s = (s + 1) & m;
+		if (e.x & 1) *n = 1, *val = e.y;          /* the value is the position word itself */
+		else *n = (uint32_t)e.y, *val = e.y >> 32; /* offset into pos[] */
+		return true;
 	}
 }
 

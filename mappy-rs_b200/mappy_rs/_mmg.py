@@ -127,12 +127,13 @@ class Lib:
         return self.L.mmg_version().decode()
 
 
-def np_from(ptr, n, dtype):
+def np_from(ptr, n, dtype, copy=True):
     if n == 0 or not ptr:
         return np.zeros(0, dtype=dtype)
     nbytes = int(n) * np.dtype(dtype).itemsize
     buf = (ctypes.c_char * nbytes).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype, count=int(n)).copy()
+    a = np.frombuffer(buf, dtype=dtype, count=int(n))
+    return a.copy() if copy else a
 
 
 class Index:
@@ -184,17 +185,31 @@ class Index:
 
 
 class Batch:
-    """Results of one mmg_map_batch call, copied into numpy arrays."""
+    """Results of one mmg_map_batch call as numpy arrays: copies by default; with own=True the arrays are
+    views of the library's result memory and this object keeps the batch handle alive (freed on close/GC)."""
 
-    def __init__(self, lib, h, n_reads):
+    def __init__(self, lib, h, n_reads, own=False):
         L = lib.L
+        self._lib, self._owned = lib, h if own else None
         nh = L.mmg_batch_n_hits(h); nc = L.mmg_batch_n_cigar(h)
-        self.hit_off = np_from(L.mmg_batch_hit_off(h), n_reads + 1, np.uint64)
-        self.hits = np_from(L.mmg_batch_hits(h), nh, HIT_DTYPE)
-        self.cigar = np_from(L.mmg_batch_cigar(h), nc, np.uint32)
+        self.hit_off = np_from(L.mmg_batch_hit_off(h), n_reads + 1, np.uint64, not own)
+        self.hits = np_from(L.mmg_batch_hits(h), nh, HIT_DTYPE, not own)
+        self.cigar = np_from(L.mmg_batch_cigar(h), nc, np.uint32, not own)
         st = np.zeros(len(STAT_NAMES), dtype=np.uint64)
         L.mmg_batch_stats(h, st.ctypes.data)
         self.stats = dict(zip(STAT_NAMES, (int(x) for x in st)))
+
+    def close(self):
+        if self._owned is not None:
+            self.hit_off = self.hits = self.cigar = None
+            self._lib.L.mmg_batch_destroy(self._owned)
+            self._owned = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def read_hits(self, i):
         return self.hits[int(self.hit_off[i]):int(self.hit_off[i + 1])]
@@ -218,11 +233,13 @@ class DeviceAligner:
     def set(self, key, v):
         self.lib.check(self.lib.L.mmg_aligner_set(self.h, key.encode(), int(v)))
 
-    def map_batch(self, buf, offs, keep_handle=False):
+    def map_batch(self, buf, offs, keep_handle=False, zero_copy=False):
         buf = np.ascontiguousarray(buf, dtype=np.uint8); offs = np.ascontiguousarray(offs, dtype=np.uint64)
         n = len(offs) - 1
         b = c_vp()
         self.lib.check(self.lib.L.mmg_map_batch(self.h, buf.ctypes.data, offs.ctypes.data, n, ctypes.byref(b)))
+        if zero_copy:
+            return Batch(self.lib, b, n, own=True)
         res = Batch(self.lib, b, n)
         if keep_handle:
             res.handle = b
