@@ -84,8 +84,9 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 		int st = 0, max_ii = -1;
 		uint64_t mii_x = 0;
 		int32_t mii_f = 0;
+		bool try_bulk = true; /* only after an anchor that had no predecessor: dense chains never pay for the test */
 		for (int i = 0; i < n; ++i) {
-			{ /* Anchors without any predecessor in range (the previous anchor is on another strand/contig or
+			if (try_bulk) { /* Anchors without any predecessor in range (the previous anchor is on another strand/contig or
 			   * more than max_dist_x behind - most index hits on a large reference) are settled 32 at a time:
 			   * f = span, p = -1, and the loop state afterwards is what the scalar path leaves: st at the
 			   * anchor itself, and the anchor as the `max_ii` candidate. */
@@ -105,6 +106,7 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 					__syncwarp();
 					continue;
 				}
+				try_bulk = false;
 			}
 			const uint64_t aix = ax[i], aiy = ay[i];
 			/* advance st: first j that shares the target strand and is within max_dist_x */
@@ -117,6 +119,7 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 				if (lead < 32) break;
 			}
 			if (i - st > max_iter) st = i - max_iter;
+			try_bulk = st == i;
 			int32_t max_f = (int32_t)(aiy >> 32 & 0xff), n_skip = 0;
 			int max_j = -1, end_j = st - 1;
 			bool broke = false;

@@ -104,13 +104,13 @@ static __device__ void dev_radix_sort_t(uint64_t *x, YT *y, int n, int *bkt, int
  * the insertion sorts of the leaf ranges (one leaf per lane) run in parallel; only the cycle-leader permutation of
  * a pass, which has no parallel form, stays on lane 0.  Ranges are disjoint, so the order in which they are
  * processed does not change the result.  bkt must be shared memory (atomics), 512 ints. */
-template<typename YT>
+template<typename YT, bool LEAF_SORT = true>
 static __device__ void dev_radix_sort_warp(uint64_t *x, YT *y, int n, int *bkt, int *stk)
 {
 	const int lane = mmg_lane();
 	const uint32_t lt = mmg_lanemask_lt();
 	if (n <= 64) {
-		if (lane == 0) dev_insertsort_t(x, y, 0, n);
+		if (LEAF_SORT && lane == 0) dev_insertsort_t(x, y, 0, n);
 		__syncwarp();
 		return;
 	}
@@ -189,7 +189,7 @@ static __device__ void dev_radix_sort_warp(uint64_t *x, YT *y, int n, int *bkt, 
 				const uint32_t pm = __ballot_sync(MMG_FULL, push);
 				if (push) { const int q = sp + __popc(pm & lt); stk[3 * q] = start, stk[3 * q + 1] = e, stk[3 * q + 2] = s2; }
 				sp += __popc(pm);
-				if (sz > 1 && sz <= 64) dev_insertsort_t(x, y, start, e);
+				if (LEAF_SORT && sz > 1 && sz <= 64) dev_insertsort_t(x, y, start, e);
 			}
 		}
 		__syncwarp();

@@ -163,7 +163,7 @@ static int alloc_arenas(mmg_aligner *al)
 	AL(c.cx, A); AL(c.cy, A); AL(c.u, A);
 	AL(c.n_u, R); AL(c.n_v, R); AL(c.r_off, R + 1);
 	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
-	AL(c.work, 64); AL(c.flags, R); AL(c.big_list, R);
+	AL(c.work, 64); AL(c.flags, R); AL(c.big_list, R); AL(c.tie_list, R);
 	AL(al->rmq_nodes, (2 * A + 2 * R + 2) * RMQ_NODE_BYTES);
 	if (al->mo.flag & MMG_F_CIGAR) {
 		ExtBufs &x = al->xb;
@@ -507,9 +507,9 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 			if (s1 == s0) { mmg_set_error("read %u has %llu anchors, more than anchor_cap", r0 + s0, (unsigned long long)(h_aoff[s0 + 1] - h_aoff[s0])); return MMG_ENOMEM; }
 			c.a_off0 = h_aoff[s0];
 		}
-		if (wi + 10 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
+		if (wi + 12 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
 		STAGE_BEGIN(); launch_expand(c, al->di, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_EXPAND);
-		STAGE_BEGIN(); launch_sort(c, al->di, s0, s1, al->n_sms, st, work + wi); wi += 3; STAGE_END(ST_SORT);
+		STAGE_BEGIN(); launch_sort(c, al->di, s0, s1, al->n_sms, st, work + wi); wi += 5; STAGE_END(ST_SORT);
 		STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
 		STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
 		STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);

@@ -142,6 +142,21 @@ __device__ __forceinline__ uint64_t rsort_record(uint64_t x, uint32_t i, const u
 }
 
 /* sorts the n keys srcx[] (stable); afterwards A[0..n) holds the records in order.  Returns the buffer holding them. */
+/* lanes of the warp that hold the same 8-bit digit (and the same validity): nine ballots, cheaper than
+ * __match_any_sync, which the compiler expands into a loop */
+__device__ __forceinline__ uint32_t rsort_peers(uint32_t d, bool valid)
+{
+	uint32_t peers = __ballot_sync(MMG_FULL, valid);
+	if (!valid) peers = ~peers;
+#pragma unroll
+	for (int b = 0; b < 8; ++b) {
+		const bool bit = (d >> b) & 1u;
+		const uint32_t bal = __ballot_sync(MMG_FULL, bit);
+		peers &= bit ? bal : ~bal;
+	}
+	return peers;
+}
+
 static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64_t *seq_off, uint64_t *A, uint64_t *B, uint32_t *cnt, uint32_t *s_red)
 {
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -171,8 +186,8 @@ static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64
 		for (int b0 = beg; b0 < end; b0 += 32) {
 			const int i = b0 + lane;
 			const bool valid = i < end;
-			const uint32_t d = valid ? (uint32_t)(A[i] >> shift) & 0xffu : 256u;
-			const uint32_t peers = __match_any_sync(MMG_FULL, d);
+			const uint32_t d = valid ? (uint32_t)(A[i] >> shift) & 0xffu : 0u;
+			const uint32_t peers = rsort_peers(d, valid);
 			if (valid && (peers & lt) == 0) cnt[w * 256 + d] += (uint32_t)__popc(peers);
 			__syncwarp();
 		}
@@ -198,8 +213,8 @@ static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64
 			const int i = b0 + lane;
 			const bool valid = i < end;
 			const uint64_t rec = valid ? A[i] : 0;
-			const uint32_t d = valid ? (uint32_t)(rec >> shift) & 0xffu : 256u;
-			const uint32_t peers = __match_any_sync(MMG_FULL, d);
+			const uint32_t d = valid ? (uint32_t)(rec >> shift) & 0xffu : 0u;
+			const uint32_t peers = rsort_peers(d, valid);
 			const uint32_t base = valid ? cnt[w * 256 + d] : 0;
 			__syncwarp();
 			if (valid && (peers & lt) == 0) cnt[w * 256 + d] = base + (uint32_t)__popc(peers);
@@ -212,9 +227,17 @@ static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64
 	return A;
 }
 
+/* TIE = false: reads of big_list; a read with equal keys (above upstream's insertion-sort size) is appended to
+ * tie_list.  TIE = true: reads of tie_list: upstream's unstable radix passes are replayed by one warp over
+ * (key, source index) staged in shared memory (the cycle-leader permutation is a chain of dependent accesses: the
+ * latency of shared memory instead of L2), the stable leaf insertion sorts are replaced by a second radix sort on
+ * (key, position after those passes) - see the tie path of sort_kernel. */
+#define RSORT_TIE_TILE 8192
+template<bool TIE>
 __global__ void __launch_bounds__(RSORT_WARPS * 32)
-radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uint32_t *list, const uint32_t *n_list)
+radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uint32_t *list, const uint32_t *n_list, uint32_t *tie_list, uint32_t *n_tie)
 {
+	MMG_DYN_SMEM(smem_raw);
 	__shared__ uint32_t s_item;
 	__shared__ int s_tie;
 	__shared__ int s_bkt[512];
@@ -233,7 +256,19 @@ radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uin
 		uint64_t *bx = c.bx + ab, *by = c.by + ab;
 		uint64_t *zx = c.zx + 2 * ab, *zy = c.zy + 2 * ab;
 		const uint64_t *srcx = ax, *srcy = ay;
-		for (int pass = 0; pass < 2 && n > 1; ++pass) {
+		if (TIE) {
+			uint64_t *kx = n <= RSORT_TIE_TILE ? (uint64_t*)smem_raw : zx;
+			uint32_t *ki = n <= RSORT_TIE_TILE ? (uint32_t*)((uint64_t*)smem_raw + RSORT_TIE_TILE) : (uint32_t*)(zx + n);
+			for (int i = tid; i < n; i += nt) kx[i] = ax[i], ki[i] = (uint32_t)i;
+			__syncthreads();
+			if (tid < 32) dev_radix_sort_warp<uint32_t, false>(kx, ki, n, s_bkt, c.f + ab);
+			__syncthreads();
+			for (int i = tid; i < n; i += nt) zy[i] = kx[i], zy[n + i] = ay[ki[i]];
+			if (tid == 0) c.flags[r] |= 1u;
+			__syncthreads();
+			srcx = zy, srcy = zy + n;
+		}
+		if (n > 1) {
 			const uint64_t *S = rsort_read(srcx, n, seq_off, zx, zx + n, s_cnt, s_red);
 			int tie = 0;
 			for (int i = tid; i < n; i += nt) {
@@ -242,22 +277,9 @@ radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uin
 				bx[i] = srcx[j], by[i] = srcy[j];
 				if (i + 1 < n && (S[i + 1] >> RSORT_IDX_BITS) == (rec >> RSORT_IDX_BITS)) tie = 1;
 			}
-			if (pass == 0 && tie && n > 64) s_tie = 1;
+			if (!TIE && tie && n > 64) s_tie = 1;
 			__syncthreads();
-			if (pass == 1 || !s_tie) break;
-			/* equal keys: replay upstream's unstable radix passes on one thread, then sort again stably
-			 * by (key, position after those passes) - see the tie path of sort_kernel */
-			uint32_t *ki = (uint32_t*)(zx + n);
-			for (int i = tid; i < n; i += nt) zx[i] = ax[i], ki[i] = (uint32_t)i;
-			__syncthreads();
-			if (tid == 0) {
-				dev_radix_sort_t<uint32_t, false>(zx, ki, n, s_bkt, c.f + ab);
-				c.flags[r] |= 1u;
-			}
-			__syncthreads();
-			for (int i = tid; i < n; i += nt) zy[i] = zx[i], zy[n + i] = ay[ki[i]];
-			__syncthreads();
-			srcx = zy, srcy = zy + n;
+			if (!TIE && s_tie && tid == 0) tie_list[atomicAdd(n_tie, 1u)] = r;
 		}
 		if (n == 1 && tid == 0) bx[0] = ax[0], by[0] = ay[0];
 		__syncthreads();
@@ -269,12 +291,20 @@ void mmg_sort_set_small_max(int v) { g_sort_small_max = v < 0 ? 0 : v > SORT_SMA
 
 int launch_sort(const ChunkDev &c, const DevIndex &di, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work)
 {
-	/* work[0]: read counter of the small pass, work[1]: length of big_list, work[2]: list counter of the radix pass */
+	/* work[0]: read counter of the small pass, work[1]: length of big_list, work[2]: list counter of the radix pass,
+	 * work[3]: length of tie_list, work[4]: list counter of the tie pass */
 	const size_t smem_small = (size_t)SORT_SMALL_ELEMS * 12;
 	int grid = n_sms * 8, need = (int)(r1 - r0);
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
 	MMG_LAUNCH((sort_kernel<SORT_SMALL_ELEMS, false>), grid, SORT_THREADS, smem_small, st, c, r0, r1, work, c.big_list, work + 1, g_sort_small_max);
-	MMG_LAUNCH(radix_sort_kernel, grid, RSORT_WARPS * 32, 0, st, c, di.seq_off, work + 2, (const uint32_t*)c.big_list, (const uint32_t*)(work + 1));
+	MMG_LAUNCH((radix_sort_kernel<false>), grid, RSORT_WARPS * 32, 0, st, c, di.seq_off, work + 2, (const uint32_t*)c.big_list, (const uint32_t*)(work + 1), c.tie_list, work + 3);
+	const size_t smem_tie = (size_t)RSORT_TIE_TILE * 12;
+	static bool attr_done = false;
+	if (!attr_done) { cudaFuncSetAttribute(radix_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tie); attr_done = true; }
+	grid = n_sms * 2;
+	if (grid > need) grid = need;
+	if (grid < 1) grid = 1;
+	MMG_LAUNCH((radix_sort_kernel<true>), grid, RSORT_WARPS * 32, smem_tie, st, c, di.seq_off, work + 4, (const uint32_t*)c.tie_list, (const uint32_t*)(work + 3), c.tie_list, work + 3);
 	return 0;
 }
