@@ -285,22 +285,29 @@ __device__ __forceinline__ int32_t dev_for_qpos(int32_t qlen, uint64_t x, uint64
 	return v;
 }
 
+/* Called by the whole warp.  Upstream walks the read's minimizers j and the region's anchors k together and
+ * advances k when anchor k sits at minimizer j; if anchor k is at none of the remaining minimizers the walk ends
+ * with k stuck.  Query positions increase along both lists, so anchor k matches exactly when its position occurs
+ * among the minimizers: 32 anchors are looked up per step by binary search, and the walk ends at the first one
+ * that is absent - the same n_match and the same last matched minimizer `en`. */
 static __device__ void dev_est_err(const DevIndex &di, int qlen, int n_regs, DevReg *regs, const uint64_t *ax, const uint64_t *ay, int n, const uint32_t *sq, const uint32_t *sm)
 {
 	if (n == 0) return;
-	uint64_t sum_k = 0;
-	for (int i = 0; i < n; ++i) sum_k += sm[i] >> 8 & 0xff;
-	const float avg_k = __fdiv_rn((float)sum_k, (float)n);
+	const int lane = mmg_lane();
+	unsigned sum_k = 0;
+	for (int i = lane; i < n; i += 32) sum_k += sm[i] >> 8 & 0xff;
+	sum_k = __reduce_add_sync(MMG_FULL, sum_k);
+	const float avg_k = __fdiv_rn((float)(uint64_t)sum_k, (float)n);
 	for (int i = 0; i < n_regs; ++i) {
 		DevReg *r = &regs[i];
-		int32_t st, en, j, k, n_match, n_tot, l_ref;
 		const bool rev = REG_REV(*r);
-		r->div = -1.0f;
-		if (r->cnt == 0) continue;
+		const int cnt = r->cnt, as = r->as;
+		if (lane == 0) r->div = -1.0f;
+		if (cnt == 0) continue;
+		int32_t st = -1;
 		{
-			int a0 = rev ? r->as + r->cnt - 1 : r->as;
+			int a0 = rev ? as + cnt - 1 : as;
 			int32_t x = dev_for_qpos(qlen, ax[a0], ay[a0]), L = 0, R = n - 1;
-			st = -1;
 			while (L <= R) {
 				int32_t m = (int32_t)(((uint64_t)L + R) >> 1);
 				int32_t y = (int32_t)(sq[m] >> 1);
@@ -309,19 +316,41 @@ static __device__ void dev_est_err(const DevIndex &di, int qlen, int n_regs, Dev
 				else { st = m; break; }
 			}
 		}
-		en = st;
 		if (st < 0) continue;
-		l_ref = (int32_t)di.seq_len[r->rid];
-		for (k = 1, j = st + 1, n_match = 1; j < n && k < r->cnt; ++j) {
-			int a1 = rev ? r->as + r->cnt - 1 - k : r->as + k;
-			int32_t x = dev_for_qpos(qlen, ax[a1], ay[a1]);
-			if (x == (int32_t)(sq[j] >> 1)) ++k, en = j, ++n_match;
+		int32_t en = st, n_match = 1;
+		for (int k0 = 1; k0 < cnt; k0 += 32) {
+			const int k = k0 + lane;
+			int32_t found = -1;
+			if (k < cnt) {
+				const int a1 = rev ? as + cnt - 1 - k : as + k;
+				const int32_t x = dev_for_qpos(qlen, ax[a1], ay[a1]);
+				int32_t L = st + 1, R = n - 1;
+				while (L <= R) {
+					int32_t m = (int32_t)(((uint64_t)L + R) >> 1);
+					int32_t y = (int32_t)(sq[m] >> 1);
+					if (y < x) L = m + 1;
+					else if (y > x) R = m - 1;
+					else { found = m; break; }
+				}
+			}
+			const uint32_t miss = __ballot_sync(MMG_FULL, k < cnt && found < 0);
+			const uint32_t have = __ballot_sync(MMG_FULL, k < cnt);
+			const int good = miss ? __ffs((int)miss) - 1 : __popc(have); /* leading anchors of this step that matched */
+			if (good > 0) {
+				n_match += good;
+				en = __shfl_sync(MMG_FULL, found, good - 1);
+			}
+			if (miss) break;
 		}
-		n_tot = en - st + 1;
-		if ((float)r->qs > avg_k && (float)r->rs > avg_k) ++n_tot;
-		if ((float)(qlen - r->qs) > avg_k && (float)(l_ref - r->re) > avg_k) ++n_tot;
-		r->div = n_match >= n_tot ? 0.0f : (float)(1.0 - pow((double)n_match / n_tot, 1.0 / (double)avg_k));
+		if (lane == 0) {
+			const int32_t l_ref = (int32_t)di.seq_len[r->rid];
+			int32_t n_tot = en - st + 1;
+			if ((float)r->qs > avg_k && (float)r->rs > avg_k) ++n_tot;
+			if ((float)(qlen - r->qs) > avg_k && (float)(l_ref - r->re) > avg_k) ++n_tot;
+			r->div = n_match >= n_tot ? 0.0f : (float)(1.0 - pow((double)n_match / n_tot, 1.0 / (double)avg_k));
+		}
 	}
+	__syncwarp();
 }
 
 /* hit.c: mm_set_inv_mapq -- an inversion takes the smaller mapq of its two neighbours on the target */

@@ -45,8 +45,14 @@ regs_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint64_
 					dev_set_parent(o.mask_level, o.mask_len, n_regs, regs, o.a * 2 + o.b, o.alt_drop, zx, (int*)zy);
 					dev_select_sub(o.pri_ratio, di.k * 2, o.best_n, 1, (int)(o.max_gap * 0.8), &n_regs, regs, (int*)zy);
 				}
+			}
+			n_regs = __shfl_sync(MMG_FULL, n_regs, 0);
+			__syncwarp();
+			{
 				const uint64_t base = c.off[r] - c.off0;
 				dev_est_err(di, qlen, n_regs, regs, ax, ay, (int)c.n_seed[r], c.sd_qpos + base, c.sd_meta + base);
+			}
+			if (lane == 0) {
 				n_regs = dev_filter_strand_retained(n_regs, regs);
 				if (!(o.flag & MMG_F_CIGAR))
 					dev_set_mapq(n_regs, regs, o.min_chain_score, o.a, c.rep_len[r]);

@@ -19,23 +19,37 @@
 
 #define SEED_NCNT 1024          /* query-occurrence counters per warp */
 #define MAX_MAX_HIGH_OCC 128    /* seed.c */
+#define SEED_UNROLL 4
 
 /* index.c mm_idx_get on the flat table: linear probing that starts at an even slot and reads the slot pair of
  * one 32-byte sector per round trip (load factor <= 0.25: a miss - most minimizers of a noisy read - almost
- * always ends at the first pair) */
-__device__ __forceinline__ bool dev_idx_get(const DevIndex &di, uint64_t minier, uint32_t *n, uint64_t *val)
+ * always ends at the first pair).  The first pair is loaded by dev_idx_probe so that a warp can have several
+ * independent probes in flight before it looks at any of them. */
+struct IdxProbe { mmg_u128 e0, e1; uint64_t s; };
+
+__device__ __forceinline__ IdxProbe dev_idx_probe(const DevIndex &di, uint64_t minier)
+{
+	IdxProbe p;
+	p.s = ((minier * 0x9E3779B97F4A7C15ULL) >> (64 - di.hbits)) & ~(uint64_t)1;
+	p.e0 = di.htab[p.s], p.e1 = di.htab[p.s + 1];
+	return p;
+}
+
+__device__ __forceinline__ bool dev_idx_resolve(const DevIndex &di, uint64_t minier, IdxProbe p, uint32_t *n, uint64_t *val)
 {
 	const uint64_t m = ((uint64_t)1 << di.hbits) - 1;
-	uint64_t s = ((minier * 0x9E3779B97F4A7C15ULL) >> (64 - di.hbits)) & ~(uint64_t)1;
 	for (;;) {
-		const mmg_u128 e0 = di.htab[s], e1 = di.htab[s + 1];
 		mmg_u128 e;
-		if (e0.x == MMG_INF64) return false;
-		if (e0.x >> 1 == minier) e = e0;
+		if (p.e0.x == MMG_INF64) return false;
+		if (p.e0.x >> 1 == minier) e = p.e0;
 		else {
-			if (e1.x == MMG_INF64) return false;
-			if (e1.x >> 1 != minier) { s = (s + 2) & m; continue; }
-			e = e1;
+			if (p.e1.x == MMG_INF64) return false;
+			if (p.e1.x >> 1 != minier) {
+				p.s = (p.s + 2) & m;
+				p.e0 = di.htab[p.s], p.e1 = di.htab[p.s + 1];
+				continue;
+			}
+			e = p.e1;
 		}
 		if (e.x & 1) *n = 1, *val = e.y;          /* the value is the position word itself */
 		else *n = (uint32_t)e.y, *val = e.y >> 32; /* offset into pos[] */
@@ -88,7 +102,7 @@ __device__ void dev_seed_select(int n, const uint32_t *sn, const uint32_t *sq, u
 	}
 }
 
-__global__ void __launch_bounds__(SEED_WARPS * 32)
+__global__ void __launch_bounds__(SEED_WARPS * 32, 3)
 seed_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 {
 	__shared__ uint32_t s_cnt[SEED_WARPS][SEED_NCNT];
@@ -153,26 +167,46 @@ seed_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 		uint64_t *sv = c.sd_val + base;
 		uint32_t *sn = c.sd_n + base, *sq = c.sd_qpos + base, *sm = c.sd_meta + base;
 		int n_m0 = 0, n_high = 0;
-		for (int i0 = 0; i0 < n; i0 += 32) {
-			int i = i0 + lane;
-			bool hit = false;
-			uint32_t hn = 0, meta = 0;
-			uint64_t hv = 0, x = 0;
-			if (i < n) {
-				x = mx[i];
-				hit = dev_idx_get(di, x >> 8, &hn, &hv);
-				if (hit) {
-					bool tandem = (i > 0 && mx[i - 1] >> 8 == x >> 8) || (i < n - 1 && mx[i + 1] >> 8 == x >> 8);
-					meta = (uint32_t)(x & 0xff) << 8 | (tandem ? 1u : 0u);
+		for (int i0 = 0; i0 < n; i0 += 32 * SEED_UNROLL) { /* SEED_UNROLL x 32 table probes in flight per warp */
+			uint64_t xs[SEED_UNROLL];
+			IdxProbe pr[SEED_UNROLL];
+#pragma unroll
+			for (int u = 0; u < SEED_UNROLL; ++u) {
+				const int i = i0 + 32 * u + lane;
+				xs[u] = i < n ? mx[i] : 0;
+			}
+#pragma unroll
+			for (int u = 0; u < SEED_UNROLL; ++u) {
+				const int i = i0 + 32 * u + lane;
+				if (i < n) pr[u] = dev_idx_probe(di, xs[u] >> 8);
+			}
+#pragma unroll
+			for (int u = 0; u < SEED_UNROLL; ++u) {
+				const int i = i0 + 32 * u + lane;
+				if (i0 + 32 * u >= n) break;
+				bool hit = false;
+				uint32_t hn = 0, meta = 0;
+				uint64_t hv = 0;
+				const uint64_t x = xs[u];
+				/* neighbours for the tandem flag: from the adjacent lanes, the warp's edges from memory */
+				uint64_t xp = __shfl_up_sync(MMG_FULL, x, 1), xn = __shfl_down_sync(MMG_FULL, x, 1);
+				if (i < n) {
+					if (lane == 0 && i > 0) xp = mx[i - 1];
+					if (lane == 31 && i < n - 1) xn = mx[i + 1];
+					hit = dev_idx_resolve(di, x >> 8, pr[u], &hn, &hv);
+					if (hit) {
+						bool tandem = (i > 0 && xp >> 8 == x >> 8) || (i < n - 1 && xn >> 8 == x >> 8);
+						meta = (uint32_t)(x & 0xff) << 8 | (tandem ? 1u : 0u);
+					}
 				}
+				uint32_t hm = __ballot_sync(MMG_FULL, hit);
+				if (hit) {
+					int d = n_m0 + __popc(hm & lt);
+					sv[d] = hv, sn[d] = hn, sq[d] = my[i], sm[d] = meta;
+				}
+				n_m0 += __popc(hm);
+				n_high += __popc(__ballot_sync(MMG_FULL, hit && (int)hn > o.mid_occ));
 			}
-			uint32_t hm = __ballot_sync(MMG_FULL, hit);
-			if (hit) {
-				int d = n_m0 + __popc(hm & lt);
-				sv[d] = hv, sn[d] = hn, sq[d] = my[i], sm[d] = meta;
-			}
-			n_m0 += __popc(hm);
-			n_high += __popc(__ballot_sync(MMG_FULL, hit && (int)hn > o.mid_occ));
 		}
 		__syncwarp();
 
@@ -328,7 +362,7 @@ scan_u32_kernel(const uint32_t *in, uint64_t *out, uint32_t n)
 
 int launch_seed(const ChunkDev &c, const DevIndex &di, const DevOpt &o, int n_sms, cudaStream_t st, uint32_t *work)
 {
-	int grid = n_sms * 4, need = ((int)c.n_reads + SEED_WARPS - 1) / SEED_WARPS;
+	int grid = n_sms * 5, need = ((int)c.n_reads + SEED_WARPS - 1) / SEED_WARPS;
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
 	MMG_LAUNCH(seed_kernel, grid, SEED_WARPS * 32, 0, st, c, di, o, work);

@@ -142,14 +142,15 @@ __device__ __forceinline__ uint64_t rsort_record(uint64_t x, uint32_t i, const u
 }
 
 /* sorts the n keys srcx[] (stable); afterwards A[0..n) holds the records in order.  Returns the buffer holding them. */
-/* lanes of the warp that hold the same 8-bit digit (and the same validity): nine ballots, cheaper than
+/* lanes of the warp that hold the same 8-bit digit (and the same validity): one ballot per varying bit, cheaper than
  * __match_any_sync, which the compiler expands into a loop */
-__device__ __forceinline__ uint32_t rsort_peers(uint32_t d, bool valid)
+__device__ __forceinline__ uint32_t rsort_peers(uint32_t d, bool valid, uint32_t vary)
 {
 	uint32_t peers = __ballot_sync(MMG_FULL, valid);
 	if (!valid) peers = ~peers;
-#pragma unroll
-	for (int b = 0; b < 8; ++b) {
+	while (vary) { /* only the bits of the digit that differ somewhere in the read (uniform over the CTA) */
+		const int b = __ffs((int)vary) - 1;
+		vary &= vary - 1;
 		const bool bit = (d >> b) & 1u;
 		const uint32_t bal = __ballot_sync(MMG_FULL, bit);
 		peers &= bit ? bal : ~bal;
@@ -180,14 +181,15 @@ static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64
 	const int chunk = ((n + RSORT_WARPS - 1) / RSORT_WARPS + 31) & ~31;
 	const int beg = w * chunk < n ? w * chunk : n, end = beg + chunk < n ? beg + chunk : n;
 	for (int shift = RSORT_IDX_BITS; shift < 64; shift += 8) {
-		if (((diff >> shift) & 0xff) == 0) continue;
+		const uint32_t vary = (uint32_t)(diff >> shift) & 0xffu;
+		if (vary == 0) continue;
 		for (int j = tid; j < RSORT_WARPS * 256; j += RSORT_WARPS * 32) cnt[j] = 0;
 		__syncthreads();
 		for (int b0 = beg; b0 < end; b0 += 32) {
 			const int i = b0 + lane;
 			const bool valid = i < end;
 			const uint32_t d = valid ? (uint32_t)(A[i] >> shift) & 0xffu : 0u;
-			const uint32_t peers = rsort_peers(d, valid);
+			const uint32_t peers = rsort_peers(d, valid, vary);
 			if (valid && (peers & lt) == 0) cnt[w * 256 + d] += (uint32_t)__popc(peers);
 			__syncwarp();
 		}
@@ -214,7 +216,7 @@ static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64
 			const bool valid = i < end;
 			const uint64_t rec = valid ? A[i] : 0;
 			const uint32_t d = valid ? (uint32_t)(rec >> shift) & 0xffu : 0u;
-			const uint32_t peers = rsort_peers(d, valid);
+			const uint32_t peers = rsort_peers(d, valid, vary);
 			const uint32_t base = valid ? cnt[w * 256 + d] : 0;
 			__syncwarp();
 			if (valid && (peers & lt) == 0) cnt[w * 256 + d] = base + (uint32_t)__popc(peers);
