@@ -220,6 +220,12 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	al->arenas_ready = false;
 	al->profile = 0;
 	al->cap_bases = (uint64_t)96 << 20, al->cap_reads = 1u << 17, al->cap_anchors = (uint64_t)48 << 20, al->cap_regs = (uint64_t)4 << 20;
+	if (prop.totalGlobalMem >= ((size_t)120 << 30) && !(mo->flag & MMG_F_CIGAR)) {
+		/* B200 (180 GB): mapping-only chunks of 384 Mbases / 256 M anchors (~60 GB of arenas).  Every stage kernel
+		 * ends with a tail of a few long-running reads (long reads, equal-key replays); fewer, larger chunks pay
+		 * that tail fewer times per batch. */
+		al->cap_bases = (uint64_t)384 << 20, al->cap_reads = 1u << 19, al->cap_anchors = (uint64_t)256 << 20, al->cap_regs = (uint64_t)16 << 20;
+	}
 	al->cap_tb = (uint64_t)32 << 30, al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48, al->big_per_warp = (uint64_t)1 << 20;
 	memset(&al->xb, 0, sizeof(al->xb));
 	al->cg_read_off = 0;
