@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32)
 chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 {
 	const int lane = mmg_lane();
+	const uint32_t lt = mmg_lanemask_lt();
 	unsigned long long tot_iter = 0, tot_anchor = 0;
 	for (;;) {
 		uint32_t r = r0 + mmg_next_item(work);
@@ -135,24 +136,43 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 				if (ok && pj >= 0) t[pj] = i;
 				__syncwarp();
 				const bool marked = ok && t[j] == i;
-				/* would lane improve max_f?  exclusive prefix max over earlier lanes and the carried max_f */
-				int32_t incl = sc;
+				/* would lane improve max_f?  Only lanes up to the first lane that holds the step's maximum can:
+				 * if that is lane 0 (the usual case in a colinear chain: the nearest predecessor scores best), or
+				 * the maximum does not beat the carried max_f, no scan is needed; otherwise an exclusive prefix
+				 * max over earlier lanes and the carried max_f decides. */
+				const int32_t mxs = __reduce_max_sync(MMG_FULL, sc);
+				const uint32_t top = __ballot_sync(MMG_FULL, sc == mxs);
+				bool improve;
+				if (mxs <= max_f) improve = false;
+				else if (top & 1u) improve = lane == 0;
+				else {
+					int32_t incl = sc;
 #pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					int32_t v = __shfl_up_sync(MMG_FULL, incl, d);
-					if (lane >= d && v > incl) incl = v;
+					for (int d = 1; d < 32; d <<= 1) {
+						int32_t v = __shfl_up_sync(MMG_FULL, incl, d);
+						if (lane >= d && v > incl) incl = v;
+					}
+					int32_t excl = __shfl_up_sync(MMG_FULL, incl, 1);
+					if (lane == 0 || excl < max_f) excl = max_f;
+					improve = ok && sc > excl;
 				}
-				int32_t excl = __shfl_up_sync(MMG_FULL, incl, 1);
-				if (lane == 0 || excl < max_f) excl = max_f;
-				const bool improve = ok && sc > excl;
-				const uint32_t I = __ballot_sync(MMG_FULL, improve), M = __ballot_sync(MMG_FULL, marked && !improve);
+				const bool mk = marked && !improve;
+				const uint32_t I = __ballot_sync(MMG_FULL, improve), M = __ballot_sync(MMG_FULL, mk);
 				int brk = -1;
 				if (M == 0) { n_skip -= __popc(I); if (n_skip < 0) n_skip = 0; }
-				else {
+				else if (I < (M & (0u - M))) {
+					/* every improving lane precedes every marked lane: n_skip drops first, then only counts up */
+					int32_t n0 = n_skip - __popc(I);
+					if (n0 < 0) n0 = 0;
+					const int need = max_skip - n0 + 1; /* the marked lane at which n_skip exceeds max_skip */
+					if (__popc(M) >= need) {
+						const uint32_t at = __ballot_sync(MMG_FULL, mk && __popc(M & (lt | (1u << lane))) == need);
+						brk = __ffs((int)at) - 1;
+					} else n_skip = n0 + __popc(M);
+				} else {
 					/* every lane is a map x -> max(x + sa, sc): improving = (-1, 0), marked = (+1, -inf),
 					 * otherwise the identity; maps of this form are closed under composition, so an
 					 * inclusive warp scan gives n_skip after every lane */
-					const bool mk = marked && !improve;
 					int32_t sa = improve ? -1 : mk ? 1 : 0, sc2 = improve ? 0 : -(1 << 28);
 #pragma unroll
 					for (int d = 1; d < 32; d <<= 1) {

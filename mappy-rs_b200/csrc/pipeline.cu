@@ -583,16 +583,24 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	return MMG_OK;
 }
 
-static void cut_chunks(const mmg_aligner *al, const mmg_batch *b, std::vector<uint32_t> &cuts)
+/* ramp: streamed mode starts with small chunks (1/8, 1/4, 1/2 of the arena) so that the first kernels start after
+ * a short copy-in and the copy of every later chunk hides behind the compute of its predecessor */
+static void cut_chunks(const mmg_aligner *al, const mmg_batch *b, std::vector<uint32_t> &cuts, bool ramp)
 {
 	const uint32_t n = b->n_reads;
 	cuts.clear();
 	cuts.push_back(0);
+	int shift = ramp ? 3 : 0;
 	for (uint32_t r0 = 0; r0 < n;) {
 		uint32_t r1 = r0;
-		while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= al->cap_bases) ++r1;
+		const uint64_t cap = al->cap_bases >> shift;
+		while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= cap) ++r1;
+		if (r1 == r0) { /* a read longer than the ramped size (reads longer than the arena were rejected earlier) */
+			while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= al->cap_bases) ++r1;
+		}
 		cuts.push_back(r1);
 		r0 = r1;
+		if (shift > 0) --shift;
 	}
 }
 
@@ -613,7 +621,7 @@ int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 	CK(cudaEventRecord(al->ev_run0, st));
 	std::vector<uint64_t> h_aoff;
 	std::vector<uint32_t> cuts;
-	cut_chunks(al, b, cuts);
+	cut_chunks(al, b, cuts, false);
 	for (size_t k = 0; k + 1 < cuts.size(); ++k) {
 		const uint32_t r0 = cuts[k], r1 = cuts[k + 1];
 		ChunkDev c = al->cd;
@@ -672,7 +680,7 @@ static int map_batch_streamed(mmg_aligner *al, mmg_batch *b)
 	b->hit_off.assign((size_t)b->n_reads + 1, 0);
 	b->hits.reserve((size_t)b->n_reads + (b->n_reads >> 3) + 16);
 	std::vector<uint32_t> cuts;
-	cut_chunks(al, b, cuts);
+	cut_chunks(al, b, cuts, true);
 	const size_t n_chunks = cuts.size() - 1;
 	CK(cudaMemsetAsync(al->d_stats_pool, 0, MMG_N_STATS * 8, st));
 	CK(cudaEventRecord(al->ev_run0, st));
