@@ -95,6 +95,8 @@ struct ChunkDev {
 	uint32_t *n_seed; uint32_t *n_a; int32_t *rep_len;
 	uint64_t *a_off;          /* n_reads + 1 (exclusive scan of n_a) */
 	uint64_t a_off0;          /* anchor-sized arrays are sliced at a_off[r] - a_off0 (sub-range of a chunk) */
+	uint64_t *af_off;         /* n_reads + 1: scan of the anchor counts BEFORE the isolated-anchor filter */
+	uint32_t *keep_bits;      /* one bit per unfiltered anchor of a filtered read (flags bit 2), at word (af_off[r] >> 5) + r */
 	/* anchors */
 	uint64_t *ax, *ay, *bx, *by;
 	int32_t *f, *p, *t, *v;
@@ -110,7 +112,7 @@ struct ChunkDev {
 	uint32_t *work;            /* dynamic work counters, one per kernel launch */
 	uint32_t *big_list;        /* reads deferred by a kernel's small-tile pass to its large-tile pass */
 	uint32_t *tie_list;        /* reads whose anchors have equal keys (sort stage) */
-	uint32_t *flags;           /* per read: bit0 = anchor ties (exact re-sort done), bit1 = re-chained */
+	uint32_t *flags;           /* per read: bit0 = anchor ties (exact re-sort done), bit1 = re-chained, bit2 = isolated anchors dropped */
 };
 
 __device__ __forceinline__ int mmg_lane() { return threadIdx.x & 31; }

@@ -31,7 +31,8 @@ struct mmg_aligner {
 	DevOpt dopt;
 	std::vector<void*> dev_allocs;     /* index + arenas */
 	/* arena capacities */
-	uint64_t cap_bases, cap_anchors, cap_regs;
+	uint64_t cap_bases, cap_anchors, cap_regs, cap_keep_words;
+	int anchor_filter;                 /* 1 = drop isolated anchors before the sort (seed.cu anchor_filter_kernel) */
 	uint32_t cap_reads;
 	bool arenas_ready;
 	ChunkDev cd;                       /* arena pointers */
@@ -164,6 +165,7 @@ static int alloc_arenas(mmg_aligner *al)
 	AL(c.n_u, R); AL(c.n_v, R); AL(c.r_off, R + 1);
 	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
 	AL(c.work, 64); AL(c.flags, R); AL(c.big_list, R); AL(c.tie_list, R);
+	AL(c.af_off, R + 1); AL(c.keep_bits, al->cap_keep_words);
 	AL(al->rmq_nodes, (2 * A + 2 * R + 2) * RMQ_NODE_BYTES);
 	if (al->mo.flag & MMG_F_CIGAR) {
 		ExtBufs &x = al->xb;
@@ -226,6 +228,8 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 		 * that tail fewer times per batch. */
 		al->cap_bases = (uint64_t)384 << 20, al->cap_reads = 1u << 19, al->cap_anchors = (uint64_t)256 << 20, al->cap_regs = (uint64_t)16 << 20;
 	}
+	al->cap_keep_words = (uint64_t)1 << 26; /* 2^31 unfiltered anchors per chunk */
+	al->anchor_filter = 1;
 	al->cap_tb = (uint64_t)32 << 30, al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48, al->big_per_warp = (uint64_t)1 << 20;
 	memset(&al->xb, 0, sizeof(al->xb));
 	al->cg_read_off = 0;
@@ -272,6 +276,7 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 {
 	if (strcmp(key, "profile") == 0) { al->profile = (int)v; return MMG_OK; }
 	if (strcmp(key, "sort_small_max") == 0) { mmg_sort_set_small_max((int)v); return MMG_OK; }
+	if (strcmp(key, "anchor_filter") == 0) { al->anchor_filter = v != 0; return MMG_OK; }
 	if (al->arenas_ready) { mmg_set_error("arena sizes are fixed after the first batch"); return MMG_EINVAL; }
 	if (strcmp(key, "chunk_bases") == 0) al->cap_bases = (uint64_t)v;
 	else if (strcmp(key, "chunk_reads") == 0) al->cap_reads = (uint32_t)v;
@@ -498,6 +503,18 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	uint64_t a_total = 0;
 	CK(cudaMemcpyAsync(&a_total, c.a_off + c.n_reads, 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
+	/* isolated-anchor filter (exact under these conditions, see seed.cu): worth its two passes over the hits only
+	 * when reads carry many anchors, i.e. on large references */
+	if (al->anchor_filter && al->mo.min_cnt >= 2 && al->mo.min_chain_score > al->idx->k && c.n_reads > 0 &&
+	    a_total > (uint64_t)c.n_reads * 512 && (a_total >> 5) + c.n_reads + 1 <= al->cap_keep_words) {
+		STAGE_BEGIN();
+		CK(cudaMemcpyAsync(c.af_off, c.a_off, (size_t)(c.n_reads + 1) * 8, cudaMemcpyDeviceToDevice, st));
+		launch_anchor_filter(c, al->di, al->dopt, al->n_sms, st, work + wi++);
+		launch_scan_u32(c.n_a, c.a_off, c.n_reads, st);
+		STAGE_END(ST_EXPAND);
+		CK(cudaMemcpyAsync(&a_total, c.a_off + c.n_reads, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
 	const bool split = a_total > al->cap_anchors;
 	if (split) { /* the per-read offsets are only needed to cut sub-ranges */
 		h_aoff.resize(c.n_reads + 1);

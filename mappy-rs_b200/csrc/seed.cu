@@ -16,6 +16,10 @@
  */
 #include "dev_common.cuh"
 #include "stages.h"
+#ifdef MMG_EMU
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 
 #define SEED_NCNT 1024          /* query-occurrence counters per warp */
 #define MAX_MAX_HIGH_OCC 128    /* seed.c */
@@ -277,7 +281,10 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 		const uint64_t *sv = c.sd_val + base;
 		const uint32_t *sn = c.sd_n + base, *sq = c.sd_qpos + base, *sm = c.sd_meta + base;
 		uint64_t *ax = c.ax + (c.a_off[r] - c.a_off0), *ay = c.ay + (c.a_off[r] - c.a_off0);
-		uint32_t out = 0;
+		const bool filt = (c.flags[r] & 4u) != 0; /* anchor_filter_kernel dropped the isolated anchors of this read */
+		const uint32_t *bits = filt ? c.keep_bits + (c.af_off[r] >> 5) + r : 0;
+		const uint32_t lt = mmg_lanemask_lt();
+		uint32_t out = 0, full = 0; /* anchors written / anchors enumerated so far */
 		for (int i0 = 0; i0 < n_m; i0 += 32) {
 			int i = i0 + lane;
 			int cnt = i < n_m ? (int)sn[i] : 0, tot;
@@ -300,7 +307,10 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 				int s_cnt = __shfl_sync(MMG_FULL, cnt, s);
 				uint64_t s_val = __shfl_sync(MMG_FULL, val, s);
 				uint32_t s_qp = __shfl_sync(MMG_FULL, qp, s), s_meta = __shfl_sync(MMG_FULL, meta, s);
-				if (t < tot) {
+				bool keep = t < tot;
+				if (keep && filt) { const uint32_t g = full + (uint32_t)t; keep = (bits[g >> 5] >> (g & 31)) & 1u; }
+				const uint32_t km = __ballot_sync(MMG_FULL, keep);
+				if (keep) {
 					int kk = t - s_ex;
 					uint64_t rr = s_cnt == 1 ? s_val : di.pos[s_val + kk];
 					uint32_t rpos = (uint32_t)rr >> 1, span = s_meta >> 8;
@@ -313,15 +323,173 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 						y = (uint64_t)span << 32 | (uint32_t)(qlen - (int)((s_qp >> 1) + 1 - span) - 1);
 					}
 					if (s_meta & 1u) y |= 1ULL << 42; /* MM_SEED_TANDEM */
-					ax[out + t] = x, ay[out + t] = y;
+					const uint32_t d = out + (uint32_t)__popc(km & lt);
+					ax[d] = x, ay[d] = y;
 				}
+				out += (uint32_t)__popc(km);
 			}
-			out += tot;
+			full += (uint32_t)tot;
 		}
 		__syncwarp();
 	}
 }
 
+/* ---- isolated-anchor filter --------------------------------------------------------------------------------
+ * On a large reference most index hits of a read are random: anchors with no other anchor of the same strand and
+ * contig within max_dist_x on either side.  Such an anchor has an empty predecessor window in mm_lchain_dp, is in
+ * no other anchor's window, ends with f = span < min_chain_score and cnt = 1 < min_cnt, so it is in no chain, is
+ * no chain end candidate, and leaves every heuristic state of the DP (st, max_ii, n_skip, t[]) as it found it:
+ * dropping it before the sort changes nothing downstream (the re-chaining and alignment stages only see chained
+ * anchors).  One thing could notice: upstream's unstable radix sort orders EQUAL keys by the whole input
+ * permutation.  Equal keys need two minimizers of the read with the same hash, so reads with a repeated
+ * minimizer hash keep all their anchors.  The host enables the filter only if min_cnt >= 2 and
+ * min_chain_score > k.
+ * One CTA per read: (0) repeated-hash test over the read's minimizers (fingerprint set), (1) anchors are counted
+ * marked in position bins of width >= max_dist_x (two shared-memory bitmaps over 2^17 hashed bins: "occupied" and
+ * "occupied twice"; a collision only keeps more), (2) an anchor is kept if its bin is occupied twice or an
+ * adjacent bin is occupied; the keep bits go to c.keep_bits, the kept count
+ * replaces c.n_a[r]. */
+#define AF_THREADS 256
+#define AF_TAB 4096            /* words: fingerprint set of phase 0, then the two bin bitmaps (AF_TAB * 32 bins each) */
+#define AF_BIN_BITS 17
+#define AF_MAX_SEEDS 3072
+#define AF_MAX_ANCHORS 65536
+#define AF_MIN_ANCHORS 512
+
+__device__ __forceinline__ uint32_t af_bin_slot(uint64_t rr, bool rev, int shift, int delta)
+{
+	const uint64_t key = ((rr >> 32) << 1 | (uint64_t)rev) * 0x9E3779B97F4A7C15ULL + (uint64_t)(((uint32_t)rr >> 1 >> shift) + delta) * 0xD6E8FEB86659FD93ULL;
+	return (uint32_t)((key ^ (key >> 29)) * 0x9E3779B97F4A7C15ULL >> (64 - AF_BIN_BITS));
+}
+
+__device__ __forceinline__ bool af_keep(const uint32_t *occ, const uint32_t *two, uint32_t b0, uint32_t bm, uint32_t bp)
+{
+	return ((two[b0 >> 5] >> (b0 & 31)) | (occ[bm >> 5] >> (bm & 31)) | (occ[bp >> 5] >> (bp & 31))) & 1u;
+}
+
+__global__ void __launch_bounds__(AF_THREADS)
+anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
+{
+	MMG_DYN_SMEM(smem_raw);
+	uint32_t *s_tab = (uint32_t*)smem_raw, *s_two = s_tab + AF_TAB, *s_pre = s_two + AF_TAB, *s_bits = s_pre + AF_MAX_SEEDS + 1;
+	__shared__ uint32_t s_item, s_dup, s_keep, s_warp[AF_THREADS / 32];
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	unsigned long long dropped = 0;
+	for (;;) {
+		if (tid == 0) s_item = atomicAdd(work, 1u), s_dup = 0, s_keep = 0;
+		__syncthreads();
+		const uint32_t r = s_item;
+		if (r >= c.n_reads) break;
+		const uint32_t n_full = c.n_a[r];
+		const int n_m = (int)c.n_seed[r], n_mz = (int)c.n_mz[r];
+		if (n_full < AF_MIN_ANCHORS || n_full > AF_MAX_ANCHORS || n_m > AF_MAX_SEEDS || n_mz > AF_MAX_SEEDS) { __syncthreads(); continue; }
+		const uint64_t base = c.off[r] - c.off0;
+		const int qlen = (int)(c.off[r + 1] - c.off[r]);
+		/* (0) a minimizer hash that occurs twice in the read? */
+		for (int j = tid; j < AF_TAB; j += AF_THREADS) s_tab[j] = 0;
+		__syncthreads();
+		for (int i = tid; i < n_mz; i += AF_THREADS) {
+			const uint64_t h = (c.mz_x[base + i] >> 8) * 0x9E3779B97F4A7C15ULL;
+			const uint32_t fp = (uint32_t)(h >> 32) | 1u;
+			for (uint32_t sl = (uint32_t)(h >> 20) & (AF_TAB - 1);; sl = (sl + 1) & (AF_TAB - 1)) {
+				const uint32_t old = atomicCAS(&s_tab[sl], 0u, fp);
+				if (old == 0) break;
+				if (old == fp) { s_dup = 1; break; }
+			}
+		}
+		__syncthreads();
+#ifdef MMG_EMU
+		if (getenv("MMG_AF_DEBUG") && tid == 0) fprintf(stderr, "[af] read %u n_full %u n_m %d n_mz %d dup %u\n", r, n_full, n_m, n_mz, s_dup);
+#endif
+		if (s_dup) { __syncthreads(); continue; }
+		/* chaining distance of this read (map.c mm_map_frag, as chain.cu) -> bin width 2^shift >= max_dist_x */
+		int32_t max_dist_x;
+		if (o.max_gap_ref > 0) max_dist_x = o.max_gap_ref;
+		else if (o.max_frag_len > 0) { max_dist_x = o.max_frag_len - qlen; if (max_dist_x < o.max_gap) max_dist_x = o.max_gap; }
+		else max_dist_x = o.max_gap;
+		if (max_dist_x < o.bw) max_dist_x = o.bw;
+		int shift = 0;
+		while (shift < 30 && (1 << shift) <= max_dist_x) ++shift;
+		const uint64_t *sv = c.sd_val + base;
+		const uint32_t *sn = c.sd_n + base, *sq = c.sd_qpos + base;
+		/* exclusive prefix of the seed occurrence counts: anchor index of a seed's first hit */
+		for (int j = tid; j < AF_TAB; j += AF_THREADS) s_tab[j] = 0, s_two[j] = 0;
+		for (int j = tid; j < (int)((n_full + 31) >> 5); j += AF_THREADS) s_bits[j] = 0;
+		{
+			uint32_t carry = 0;
+			for (int i0 = 0; i0 < n_m; i0 += AF_THREADS) {
+				const int i = i0 + tid;
+				const uint32_t v = i < n_m ? sn[i] : 0;
+				uint32_t x = v;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					uint32_t y = __shfl_up_sync(MMG_FULL, x, d);
+					if (lane >= d) x += y;
+				}
+				if (lane == 31) s_warp[wib] = x;
+				__syncthreads();
+				uint32_t pre = carry, tot = 0;
+				for (int q = 0; q < AF_THREADS / 32; ++q) { if (q < wib) pre += s_warp[q]; tot += s_warp[q]; }
+				if (i < n_m) s_pre[i] = pre + x - v;
+				carry += tot;
+				__syncthreads();
+			}
+		}
+		__syncthreads();
+		/* (1) count, (2) decide: seeds with few hits one per thread, seeds with many hits one per warp */
+		for (int pass = 0; pass < 2; ++pass) {
+			for (int i = tid; i < n_m; i += AF_THREADS) {
+				const uint32_t cnt = sn[i];
+				if (cnt > 32) continue;
+				const uint64_t val = sv[i];
+				const uint32_t qp = sq[i];
+				for (uint32_t k = 0; k < cnt; ++k) {
+					const uint64_t rr = cnt == 1 ? val : di.pos[val + k];
+					const bool rev = (rr & 1) != (qp & 1);
+					const uint32_t b0 = af_bin_slot(rr, rev, shift, 0);
+					if (pass == 0) {
+						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+					} else if (af_keep(s_tab, s_two, b0, af_bin_slot(rr, rev, shift, -1), af_bin_slot(rr, rev, shift, 1))) {
+						const uint32_t g = s_pre[i] + k;
+						atomicOr(&s_bits[g >> 5], 1u << (g & 31));
+						atomicAdd(&s_keep, 1u);
+					}
+				}
+			}
+			for (int i = wib; i < n_m; i += AF_THREADS / 32) {
+				const uint32_t cnt = sn[i];
+				if (cnt <= 32) continue;
+				const uint64_t val = sv[i];
+				const uint32_t qp = sq[i];
+				for (uint32_t k = lane; k < cnt; k += 32) {
+					const uint64_t rr = di.pos[val + k];
+					const bool rev = (rr & 1) != (qp & 1);
+					const uint32_t b0 = af_bin_slot(rr, rev, shift, 0);
+					if (pass == 0) {
+						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+					} else if (af_keep(s_tab, s_two, b0, af_bin_slot(rr, rev, shift, -1), af_bin_slot(rr, rev, shift, 1))) {
+						const uint32_t g = s_pre[i] + k;
+						atomicOr(&s_bits[g >> 5], 1u << (g & 31));
+						atomicAdd(&s_keep, 1u);
+					}
+				}
+			}
+			__syncthreads();
+		}
+		uint32_t *bits = c.keep_bits + (c.af_off[r] >> 5) + r;
+		for (int j = tid; j < (int)((n_full + 31) >> 5); j += AF_THREADS) bits[j] = s_bits[j];
+#ifdef MMG_EMU
+		if (getenv("MMG_AF_DEBUG") && tid == 0) fprintf(stderr, "[af] read %u kept %u of %u shift %d\n", r, s_keep, n_full, shift);
+#endif
+		if (tid == 0) {
+			c.n_a[r] = s_keep;
+			c.flags[r] |= 4u;
+			dropped += n_full - s_keep;
+		}
+		__syncthreads();
+	}
+	if (tid == 0 && dropped) atomicAdd(&c.stats[4], dropped), atomicAdd(&c.stats[10], dropped); /* n_anchor counts what upstream would have sorted */
+}
 /* ---- exclusive scan of per-read counts (single block; n is a few 10^5) ---- */
 __global__ void __launch_bounds__(1024)
 scan_u32_kernel(const uint32_t *in, uint64_t *out, uint32_t n)
@@ -375,6 +543,18 @@ int launch_expand(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
 	MMG_LAUNCH(expand_kernel, grid, SEED_WARPS * 32, 0, st, c, di, o, r0, r1, work);
+	return 0;
+}
+
+int launch_anchor_filter(const ChunkDev &c, const DevIndex &di, const DevOpt &o, int n_sms, cudaStream_t st, uint32_t *work)
+{
+	int grid = n_sms * 4, need = (int)c.n_reads;
+	if (grid > need) grid = need;
+	if (grid < 1) grid = 1;
+	const size_t smem = (size_t)(2 * AF_TAB + AF_MAX_SEEDS + 1 + AF_MAX_ANCHORS / 32) * 4;
+	static bool attr_done = false;
+	if (!attr_done) { cudaFuncSetAttribute(anchor_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+	MMG_LAUNCH(anchor_filter_kernel, grid, AF_THREADS, smem, st, c, di, o, work);
 	return 0;
 }
 

@@ -14,6 +14,7 @@ enum { ST_H2D = 0, ST_SKETCH, ST_SEED, ST_SCAN, ST_EXPAND, ST_SORT, ST_CHAIN, ST
 
 int launch_sketch(const ChunkDev &c, const DevIndex &di, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_seed(const ChunkDev &c, const DevIndex &di, const DevOpt &o, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_anchor_filter(const ChunkDev &c, const DevIndex &di, const DevOpt &o, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_scan_u32(const uint32_t *in, uint64_t *out, uint32_t n, cudaStream_t st);  /* out[n] = total */
 int launch_expand(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_sort(const ChunkDev &c, const DevIndex &di, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);

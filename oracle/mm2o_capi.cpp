@@ -88,6 +88,20 @@ mm2o_aligner_t *mm2o_build(const char *preset, int n_seq, const char **names, co
 	return al;
 }
 
+/* the same with the k / w overrides of the constructor (src/lib.rs:341-346 write idxopt.k / idxopt.w) */
+mm2o_aligner_t *mm2o_build_kw(const char *preset, int k, int w, int n_seq, const char **names, const char **seqs, const uint32_t *lens)
+{
+	mm2o_aligner_t *al = new mm2o_aligner_t();
+	mm_set_opt(0, &al->io, &al->mo);
+	if (preset && preset[0] && mm_set_opt(preset, &al->io, &al->mo) < 0) { delete al; return 0; }
+	al->mo.flag |= 4;
+	if (k > 0) al->io.k = (short)k;
+	if (w > 0) al->io.w = (short)w;
+	al->mi = mm_idx_build(al->io.w, al->io.k, al->io.bucket_bits, al->io.flag, n_seq, names, seqs, lens);
+	mm_mapopt_update(&al->mo, al->mi);
+	return al;
+}
+
 void mm2o_close(mm2o_aligner_t *al) { if (al) { mm_idx_destroy(al->mi); delete al; } }
 
 int mm2o_dump_index(mm2o_aligner_t *al, const char *fn) { return mm_idx_dump(fn, al->mi); }

@@ -47,6 +47,7 @@ def lib():
     vp, cp, i32, u32, u64, i64 = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64
     L.mm2o_open.restype = vp; L.mm2o_open.argtypes = [cp, cp, i32]
     L.mm2o_build.restype = vp; L.mm2o_build.argtypes = [cp, i32, vp, vp, vp]
+    L.mm2o_build_kw.restype = vp; L.mm2o_build_kw.argtypes = [cp, i32, i32, i32, vp, vp, vp]
     L.mm2o_close.argtypes = [vp]
     L.mm2o_dump_index.argtypes = [vp, cp]
     L.mm2o_set_opt_int.argtypes = [vp, cp, i64]
@@ -107,7 +108,7 @@ class Oracle:
     """CPU restatement of minimap2 v2.26 behind mappy-rs' option plumbing
     (/root/reference/src/lib.rs:311-436)."""
 
-    def __init__(self, fn_idx_in=None, preset=None, names=None, seqs=None, **overrides):
+    def __init__(self, fn_idx_in=None, preset=None, names=None, seqs=None, k=0, w=0, **overrides):
         L = lib()
         p = preset.encode() if preset else None
         if fn_idx_in is not None:
@@ -120,7 +121,7 @@ class Oracle:
             nm = (ctypes.c_char_p * n)(*[x.encode() for x in names])
             sq = (ctypes.c_char_p * n)(*self._keep)
             ln = np.array([len(s) for s in self._keep], dtype=np.uint32)
-            self.h = L.mm2o_build(p, n, nm, sq, ln.ctypes.data)
+            self.h = L.mm2o_build_kw(p, int(k), int(w), n, nm, sq, ln.ctypes.data) if (k or w) else L.mm2o_build(p, n, nm, sq, ln.ctypes.data)
         if not self.h:
             raise RuntimeError("oracle: failed to open/build index")
         for k, v in overrides.items():

@@ -239,3 +239,46 @@ def test_radix_sort_pass_for_every_read(emu_lib, oracle_mod):
     finally:
         c.aligner.set("sort_small_max", 1024)
         c.close()
+
+
+def _random_hit_case(lib, oracle_mod, ref_len, seed):
+    """Short k-mers on a large reference: most anchors of a read are random, isolated hits (what a human-scale
+    index does to 15-mers)."""
+    ref, coff, names, seqs = parity.random_reference(seed, [ref_len])
+    c = parity.Case.__new__(parity.Case)
+    import ctypes
+    from mappy_rs import _mmg
+    c.lib = lib
+    c.io, c.mopt = _mmg.IdxOpt(), _mmg.MapOpt()
+    lib.check(lib.L.mmg_set_opt(None, ctypes.byref(c.io), ctypes.byref(c.mopt)))
+    c.io.k, c.io.w = 11, 5
+    c.oracle = oracle_mod.Oracle(names=names, seqs=seqs, k=11, w=5)
+    c.index = _mmg.Index.build(lib, c.io, names, seqs)
+    c.mopt.flag = 0
+    c.oracle.set_opt("flag", 0)
+    for k_, v in (("max_gap", 1000), ("bw", 400), ("bw_long", 400)):
+        setattr(c.mopt, k_, v)
+        c.oracle.set_opt(k_, v)
+    lib.check(lib.L.mmg_mapopt_update(ctypes.byref(c.mopt), c.index.h))
+    assert c.mopt.mid_occ == c.oracle.get_opt("mid_occ")
+    c.aligner = _mmg.DeviceAligner(lib, c.index, c.mopt)
+    return c, ref, coff
+
+
+def test_isolated_anchor_filter_is_exact(emu_lib, oracle_mod):
+    """Reads whose anchors are mostly isolated random hits: they are dropped before the sort (n_dropped > 0) and
+    every chain, region and mapq still equals the oracle's, which sorts and chains all of them."""
+    c, ref, coff = _random_hit_case(emu_lib, oracle_mod, 6000000, 97)
+    try:
+        buf, offs, _ = data_gen.make_reads(98, ref, coff, 70, 900, 1900)   # short: few repeated 11-mer hashes per read
+        b2, o2 = oracle_mod.pack_reads(_dup_reads(ref, 4, 99))             # repeated minimizers: these keep every anchor
+        buf = np.concatenate([buf, b2]); offs = np.concatenate([offs, o2[1:] + offs[-1]])
+        dev, stage_diffs = parity.compare_stages(c, buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert dev.stats["n_dropped"] > 0.2 * ora.stats["n_anchor"]
+        assert stage_diffs == [] and parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
+        c.aligner.set("anchor_filter", 0)
+        dev2 = c.aligner.map_batch(buf, offs)
+        assert dev2.stats["n_dropped"] == 0 and parity.compare_hits(dev2, ora) == []
+    finally:
+        c.close()

@@ -173,3 +173,45 @@ def test_cigar_mode_fixture_map_one(gpu_lib, oracle_mod):
         assert [(int(h["rs"]), int(h["re"])) for h in dev.hits] == [(0, 400)] * 40
     finally:
         c.close()
+
+
+def _random_hit_case(lib, oracle_mod, ref_len, seed, k, w, max_gap):
+    """Short k-mers / a large reference: most anchors of a read are isolated random hits."""
+    import ctypes
+    from mappy_rs import _mmg
+    ref, coff, names, seqs = parity.random_reference(seed, [ref_len])
+    c = parity.Case.__new__(parity.Case)
+    c.lib = lib
+    c.io, c.mopt = _mmg.IdxOpt(), _mmg.MapOpt()
+    lib.check(lib.L.mmg_set_opt(None, ctypes.byref(c.io), ctypes.byref(c.mopt)))
+    c.io.k, c.io.w = k, w
+    c.oracle = oracle_mod.Oracle(names=names, seqs=seqs, k=k, w=w)
+    c.index = _mmg.Index.build(lib, c.io, names, seqs)
+    c.mopt.flag = 0
+    c.oracle.set_opt("flag", 0)
+    if max_gap:
+        for k_, v in (("max_gap", max_gap), ("bw", 400), ("bw_long", 400)):
+            setattr(c.mopt, k_, v)
+            c.oracle.set_opt(k_, v)
+    lib.check(lib.L.mmg_mapopt_update(ctypes.byref(c.mopt), c.index.h))
+    assert c.mopt.mid_occ == c.oracle.get_opt("mid_occ")
+    c.aligner = _mmg.DeviceAligner(lib, c.index, c.mopt)
+    return c, ref, coff
+
+
+def test_isolated_anchor_filter_and_radix_sort_at_scale(gpu_lib, oracle_mod):
+    """Thousands of anchors per read, mostly isolated random hits (13-mers on 60 Mb): the filter drops them, the
+    reads that keep everything (repeated minimizer hashes) go through the CTA radix sort, and every hit still
+    equals the oracle's, which sorts and chains all anchors."""
+    c, ref, coff = _random_hit_case(gpu_lib, oracle_mod, 60_000_000, 101, 13, 5, 0)
+    try:
+        buf, offs, _ = data_gen.make_reads(102, ref, coff, 3000, 1000, 9000)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+        assert ora.stats["n_anchor"] > 1500 * 3000 and dev.stats["n_dropped"] > 0.3 * ora.stats["n_anchor"]
+        assert parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
+        c.aligner.set("anchor_filter", 0)
+        dev2 = c.aligner.map_batch(buf, offs)
+        assert dev2.stats["n_dropped"] == 0 and parity.compare_hits(dev2, ora) == []
+    finally:
+        c.close()
