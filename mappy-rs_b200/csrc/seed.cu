@@ -356,15 +356,41 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 #define AF_MAX_ANCHORS 65536
 #define AF_MIN_ANCHORS 512
 
-__device__ __forceinline__ uint32_t af_bin_slot(uint64_t rr, bool rev, int shift, int delta)
+/* hashed slot of the position bin (strand, contig, (pos >> shift) + delta) in a table of 2^bits bins */
+__device__ __forceinline__ uint32_t af_bin_slot(uint64_t rr, bool rev, int shift, int delta, uint32_t seed, int bits)
 {
-	const uint64_t key = ((rr >> 32) << 1 | (uint64_t)rev) * 0x9E3779B97F4A7C15ULL + (uint64_t)(((uint32_t)rr >> 1 >> shift) + delta) * 0xD6E8FEB86659FD93ULL;
-	return (uint32_t)((key ^ (key >> 29)) * 0x9E3779B97F4A7C15ULL >> (64 - AF_BIN_BITS));
+	const uint32_t a = ((uint32_t)(rr >> 32) << 1 | (uint32_t)rev) * 0x9E3779B1u + seed;
+	const uint32_t b = (((uint32_t)rr >> 1 >> shift) + (uint32_t)delta) * 0x85EBCA77u;
+	uint32_t h = (a ^ b) * 0xC2B2AE3Du;
+	h ^= h >> 15;
+	return (h * 0x27D4EB2Fu) >> (32 - bits);
 }
 
 __device__ __forceinline__ bool af_keep(const uint32_t *occ, const uint32_t *two, uint32_t b0, uint32_t bm, uint32_t bp)
 {
 	return ((two[b0 >> 5] >> (b0 & 31)) | (occ[bm >> 5] >> (bm & 31)) | (occ[bp >> 5] >> (bp & 31))) & 1u;
+}
+
+/* f(g, rr, rev) for every anchor of the read (g = index in seed order, rr = index position word): seeds with few
+ * hits one per thread, seeds with many hits one per warp */
+template<typename F>
+__device__ __forceinline__ void af_for_each(const DevIndex &di, int n_m, const uint64_t *sv, const uint32_t *sn, const uint32_t *sq, const uint32_t *s_pre, F f)
+{
+	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	for (int i = tid; i < n_m; i += AF_THREADS) {
+		const uint32_t cnt = sn[i];
+		if (cnt > 32) continue;
+		const uint64_t val = sv[i];
+		const uint32_t qp = sq[i], g0 = s_pre[i];
+		for (uint32_t k = 0; k < cnt; ++k) f(g0 + k, cnt == 1 ? val : di.pos[val + k], qp);
+	}
+	for (int i = wib; i < n_m; i += AF_THREADS / 32) {
+		const uint32_t cnt = sn[i];
+		if (cnt <= 32) continue;
+		const uint64_t val = sv[i];
+		const uint32_t qp = sq[i], g0 = s_pre[i];
+		for (uint32_t k = lane; k < cnt; k += 32) f(g0 + k, di.pos[val + k], qp);
+	}
 }
 
 __global__ void __launch_bounds__(AF_THREADS)
@@ -385,22 +411,22 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 		if (n_full < AF_MIN_ANCHORS || n_full > AF_MAX_ANCHORS || n_m > AF_MAX_SEEDS || n_mz > AF_MAX_SEEDS) { __syncthreads(); continue; }
 		const uint64_t base = c.off[r] - c.off0;
 		const int qlen = (int)(c.off[r + 1] - c.off[r]);
-		/* (0) a minimizer hash that occurs twice in the read? */
-		for (int j = tid; j < AF_TAB; j += AF_THREADS) s_tab[j] = 0;
+		/* (0) a minimizer hash that occurs twice in the read?  open-addressing set of 32-bit fingerprints */
+		int fbits = 9;
+		while ((1 << fbits) < 2 * n_mz) ++fbits;
+		const uint32_t fmask = (1u << fbits) - 1;
+		for (int j = tid; j <= (int)fmask; j += AF_THREADS) s_tab[j] = 0;
 		__syncthreads();
 		for (int i = tid; i < n_mz; i += AF_THREADS) {
 			const uint64_t h = (c.mz_x[base + i] >> 8) * 0x9E3779B97F4A7C15ULL;
 			const uint32_t fp = (uint32_t)(h >> 32) | 1u;
-			for (uint32_t sl = (uint32_t)(h >> 20) & (AF_TAB - 1);; sl = (sl + 1) & (AF_TAB - 1)) {
+			for (uint32_t sl = (uint32_t)(h >> 20) & fmask;; sl = (sl + 1) & fmask) {
 				const uint32_t old = atomicCAS(&s_tab[sl], 0u, fp);
 				if (old == 0) break;
 				if (old == fp) { s_dup = 1; break; }
 			}
 		}
 		__syncthreads();
-#ifdef MMG_EMU
-		if (getenv("MMG_AF_DEBUG") && tid == 0) fprintf(stderr, "[af] read %u n_full %u n_m %d n_mz %d dup %u\n", r, n_full, n_m, n_mz, s_dup);
-#endif
 		if (s_dup) { __syncthreads(); continue; }
 		/* chaining distance of this read (map.c mm_map_frag, as chain.cu) -> bin width 2^shift >= max_dist_x */
 		int32_t max_dist_x;
@@ -412,10 +438,9 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 		while (shift < 30 && (1 << shift) <= max_dist_x) ++shift;
 		const uint64_t *sv = c.sd_val + base;
 		const uint32_t *sn = c.sd_n + base, *sq = c.sd_qpos + base;
-		/* exclusive prefix of the seed occurrence counts: anchor index of a seed's first hit */
-		for (int j = tid; j < AF_TAB; j += AF_THREADS) s_tab[j] = 0, s_two[j] = 0;
-		for (int j = tid; j < (int)((n_full + 31) >> 5); j += AF_THREADS) s_bits[j] = 0;
-		{
+		const int n_words = (int)((n_full + 31) >> 5);
+		for (int j = tid; j < n_words; j += AF_THREADS) s_bits[j] = 0;
+		{ /* exclusive prefix of the seed occurrence counts: anchor index of a seed's first hit */
 			uint32_t carry = 0;
 			for (int i0 = 0; i0 < n_m; i0 += AF_THREADS) {
 				const int i = i0 + tid;
@@ -435,61 +460,46 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 				__syncthreads();
 			}
 		}
-		__syncthreads();
-		/* (1) count, (2) decide: seeds with few hits one per thread, seeds with many hits one per warp */
-		for (int pass = 0; pass < 2; ++pass) {
-			for (int i = tid; i < n_m; i += AF_THREADS) {
-				const uint32_t cnt = sn[i];
-				if (cnt > 32) continue;
-				const uint64_t val = sv[i];
-				const uint32_t qp = sq[i];
-				for (uint32_t k = 0; k < cnt; ++k) {
-					const uint64_t rr = cnt == 1 ? val : di.pos[val + k];
-					const bool rev = (rr & 1) != (qp & 1);
-					const uint32_t b0 = af_bin_slot(rr, rev, shift, 0);
-					if (pass == 0) {
-						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
-					} else if (af_keep(s_tab, s_two, b0, af_bin_slot(rr, rev, shift, -1), af_bin_slot(rr, rev, shift, 1))) {
-						const uint32_t g = s_pre[i] + k;
-						atomicOr(&s_bits[g >> 5], 1u << (g & 31));
-						atomicAdd(&s_keep, 1u);
-					}
-				}
-			}
-			for (int i = wib; i < n_m; i += AF_THREADS / 32) {
-				const uint32_t cnt = sn[i];
-				if (cnt <= 32) continue;
-				const uint64_t val = sv[i];
-				const uint32_t qp = sq[i];
-				for (uint32_t k = lane; k < cnt; k += 32) {
-					const uint64_t rr = di.pos[val + k];
-					const bool rev = (rr & 1) != (qp & 1);
-					const uint32_t b0 = af_bin_slot(rr, rev, shift, 0);
-					if (pass == 0) {
-						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
-					} else if (af_keep(s_tab, s_two, b0, af_bin_slot(rr, rev, shift, -1), af_bin_slot(rr, rev, shift, 1))) {
-						const uint32_t g = s_pre[i] + k;
-						atomicOr(&s_bits[g >> 5], 1u << (g & 31));
-						atomicAdd(&s_keep, 1u);
-					}
-				}
-			}
+		/* two rounds: the second one re-tests the survivors of the first with another hash, so that what a
+		 * collision kept by accident is (almost always) dropped after all */
+		uint32_t n_in = n_full;
+		for (int round = 0; round < 2; ++round) {
+			int bits = 12;
+			while (bits < AF_BIN_BITS && (1u << bits) < 8u * n_in) ++bits;
+			const uint32_t seed = round ? 0x68E31DA4u : 0u;
+			for (int j = tid; j < (1 << (bits - 5)); j += AF_THREADS) s_tab[j] = 0, s_two[j] = 0;
+			if (tid == 0) s_keep = 0;
+			__syncthreads();
+			af_for_each(di, n_m, sv, sn, sq, s_pre, [&](uint32_t g, uint64_t rr, uint32_t qp) {
+				if (round && !((s_bits[g >> 5] >> (g & 31)) & 1u)) return;
+				const uint32_t b0 = af_bin_slot(rr, (rr & 1) != (qp & 1), shift, 0, seed, bits);
+				if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+			});
+			__syncthreads();
+			af_for_each(di, n_m, sv, sn, sq, s_pre, [&](uint32_t g, uint64_t rr, uint32_t qp) {
+				if (round && !((s_bits[g >> 5] >> (g & 31)) & 1u)) return;
+				const bool rev = (rr & 1) != (qp & 1);
+				const bool keep = af_keep(s_tab, s_two, af_bin_slot(rr, rev, shift, 0, seed, bits), af_bin_slot(rr, rev, shift, -1, seed, bits),
+				                          af_bin_slot(rr, rev, shift, 1, seed, bits));
+				if (keep) { if (!round) atomicOr(&s_bits[g >> 5], 1u << (g & 31)); atomicAdd(&s_keep, 1u); }
+				else if (round) atomicAnd(&s_bits[g >> 5], ~(1u << (g & 31)));
+			});
+			__syncthreads();
+			n_in = s_keep;
 			__syncthreads();
 		}
-		uint32_t *bits = c.keep_bits + (c.af_off[r] >> 5) + r;
-		for (int j = tid; j < (int)((n_full + 31) >> 5); j += AF_THREADS) bits[j] = s_bits[j];
-#ifdef MMG_EMU
-		if (getenv("MMG_AF_DEBUG") && tid == 0) fprintf(stderr, "[af] read %u kept %u of %u shift %d\n", r, s_keep, n_full, shift);
-#endif
+		uint32_t *bits_out = c.keep_bits + (c.af_off[r] >> 5) + r;
+		for (int j = tid; j < n_words; j += AF_THREADS) bits_out[j] = s_bits[j];
 		if (tid == 0) {
-			c.n_a[r] = s_keep;
+			c.n_a[r] = n_in;
 			c.flags[r] |= 4u;
-			dropped += n_full - s_keep;
+			dropped += n_full - n_in;
 		}
 		__syncthreads();
 	}
 	if (tid == 0 && dropped) atomicAdd(&c.stats[4], dropped), atomicAdd(&c.stats[10], dropped); /* n_anchor counts what upstream would have sorted */
 }
+
 /* ---- exclusive scan of per-read counts (single block; n is a few 10^5) ---- */
 __global__ void __launch_bounds__(1024)
 scan_u32_kernel(const uint32_t *in, uint64_t *out, uint32_t n)
