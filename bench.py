@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- reads/s of the minimap2 mapping path behind mappy-rs `map_batch` on B200.
 
-Default workload (BASELINE.json configs[1]): 5 Mb synthetic reference (seed 1), 200 000
-simulated ONT reads of 1-10 kb with 8 % errors (seed 2), preset map-ont,
-mapping-only, one GPU.  One "step" = one pass of the whole hot path (sketch ->
-seed -> sort -> chain -> select/mapq) over the batch.  --workload human / prefix /
-hifi select configs[2] (3.1 Gb reference), configs[3] (400-base prefixes streamed in
-20k batches, with batch latency) and configs[4] (map-hifi); --cigar turns MM_F_CIGAR on.
+Default workload = the configuration BASELINE.json's metric is quoted on (configs[2]):
+3.1 Gb synthetic reference (24 contigs, seed 3; the index is built on the device),
+250 000 simulated ONT reads of 1-10 kb with 8 % errors per GPU (2 M / 8; seed 4), preset
+map-ont, mapping-only.  One "step" = one pass of the whole hot path (sketch -> seed ->
+anchor filter/expand -> sort -> chain -> select/mapq) over the batch.  --workload config1 /
+prefix / hifi select configs[1] (5 Mb reference, 200 000 reads), configs[3] (400-base
+prefixes streamed in 20k batches, with batch latency) and configs[4] (map-hifi); --cigar
+turns MM_F_CIGAR on.
 
   value     : reads/s with the reads already resident in HBM, timed by CUDA
               events on the library's stream around all kernels of a step.
@@ -17,7 +19,7 @@ hifi select configs[2] (3.1 Gb reference), configs[3] (400-base prefixes streame
   cpu_baseline / --impl reference : the oracle (CPU restatement of minimap2
               2.26; the reference itself cannot be built here)
               on all host cores over a bounded sample of the same reads.
-N > 1 (torchrun): index replicated per GPU, every rank maps its own 200k reads
+N > 1 (torchrun): index replicated per GPU (each rank builds it on its device), every rank maps its own reads
 (weak scaling), no collective on the data path; timing = max over ranks.
 """
 import argparse
@@ -331,7 +333,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default 200000; prefix workload 2000000 / 100 batches of 20000)")
-    ap.add_argument("--workload", default="config1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="human", choices=sorted(WORKLOADS),
+                    help="default: the configuration BASELINE.json's metric is quoted on (configs[2], 3.1 Gb reference; it fits one GPU)")
     ap.add_argument("--ref", default="", choices=["", "human"], help="prefix/hifi workloads: use the 3.1 Gb reference instead of the 5 Mb one")
     ap.add_argument("--ref-bases", type=int, default=3_100_000_000)
     ap.add_argument("--batch", type=int, default=20000, help="prefix workload: reads per streamed batch")

@@ -96,6 +96,7 @@ struct ChunkDev {
 	uint64_t *a_off;          /* n_reads + 1 (exclusive scan of n_a) */
 	uint64_t a_off0;          /* anchor-sized arrays are sliced at a_off[r] - a_off0 (sub-range of a chunk) */
 	uint64_t *af_off;         /* n_reads + 1: scan of the anchor counts BEFORE the isolated-anchor filter */
+	uint64_t *hit_scratch;    /* index position words of the reads the filter looked at, at af_off[r] (bit 63 = strand of the seed) */
 	uint32_t *keep_bits;      /* one bit per unfiltered anchor of a filtered read (flags bit 2), at word (af_off[r] >> 5) + r */
 	/* anchors */
 	uint64_t *ax, *ay, *bx, *by;

@@ -165,7 +165,7 @@ static int alloc_arenas(mmg_aligner *al)
 	AL(c.n_u, R); AL(c.n_v, R); AL(c.r_off, R + 1);
 	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
 	AL(c.work, 64); AL(c.flags, R); AL(c.big_list, R); AL(c.tie_list, R);
-	AL(c.af_off, R + 1); AL(c.keep_bits, al->cap_keep_words);
+	AL(c.af_off, R + 1); AL(c.keep_bits, al->cap_keep_words); AL(c.hit_scratch, al->cap_keep_words * 32);
 	AL(al->rmq_nodes, (2 * A + 2 * R + 2) * RMQ_NODE_BYTES);
 	if (al->mo.flag & MMG_F_CIGAR) {
 		ExtBufs &x = al->xb;
@@ -222,13 +222,14 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	al->arenas_ready = false;
 	al->profile = 0;
 	al->cap_bases = (uint64_t)96 << 20, al->cap_reads = 1u << 17, al->cap_anchors = (uint64_t)48 << 20, al->cap_regs = (uint64_t)4 << 20;
+	al->cap_keep_words = (uint64_t)1 << 22; /* unfiltered anchors per chunk the isolated-anchor filter can look at: 2^27, 2^29 on a 180 GB device */
 	if (prop.totalGlobalMem >= ((size_t)120 << 30) && !(mo->flag & MMG_F_CIGAR)) {
 		/* B200 (180 GB): mapping-only chunks of 384 Mbases / 256 M anchors (~60 GB of arenas).  Every stage kernel
 		 * ends with a tail of a few long-running reads (long reads, equal-key replays); fewer, larger chunks pay
 		 * that tail fewer times per batch. */
 		al->cap_bases = (uint64_t)384 << 20, al->cap_reads = 1u << 19, al->cap_anchors = (uint64_t)256 << 20, al->cap_regs = (uint64_t)16 << 20;
+		al->cap_keep_words = (uint64_t)1 << 24;
 	}
-	al->cap_keep_words = (uint64_t)1 << 26; /* 2^31 unfiltered anchors per chunk */
 	al->anchor_filter = 1;
 	al->cap_tb = (uint64_t)32 << 30, al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48, al->big_per_warp = (uint64_t)1 << 20;
 	memset(&al->xb, 0, sizeof(al->xb));

@@ -283,6 +283,7 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 		uint64_t *ax = c.ax + (c.a_off[r] - c.a_off0), *ay = c.ay + (c.a_off[r] - c.a_off0);
 		const bool filt = (c.flags[r] & 4u) != 0; /* anchor_filter_kernel dropped the isolated anchors of this read */
 		const uint32_t *bits = filt ? c.keep_bits + (c.af_off[r] >> 5) + r : 0;
+		const uint64_t *hits = filt ? c.hit_scratch + c.af_off[r] : 0; /* the index positions gathered by the filter */
 		const uint32_t lt = mmg_lanemask_lt();
 		uint32_t out = 0, full = 0; /* anchors written / anchors enumerated so far */
 		for (int i0 = 0; i0 < n_m; i0 += 32) {
@@ -312,7 +313,7 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 				const uint32_t km = __ballot_sync(MMG_FULL, keep);
 				if (keep) {
 					int kk = t - s_ex;
-					uint64_t rr = s_cnt == 1 ? s_val : di.pos[s_val + kk];
+					uint64_t rr = filt ? hits[full + (uint32_t)t] & 0x7fffffffffffffffULL : s_cnt == 1 ? s_val : di.pos[s_val + kk];
 					uint32_t rpos = (uint32_t)rr >> 1, span = s_meta >> 8;
 					uint64_t x, y;
 					if ((rr & 1) == (s_qp & 1)) { /* forward strand */
@@ -371,28 +372,6 @@ __device__ __forceinline__ bool af_keep(const uint32_t *occ, const uint32_t *two
 	return ((two[b0 >> 5] >> (b0 & 31)) | (occ[bm >> 5] >> (bm & 31)) | (occ[bp >> 5] >> (bp & 31))) & 1u;
 }
 
-/* f(g, rr, rev) for every anchor of the read (g = index in seed order, rr = index position word): seeds with few
- * hits one per thread, seeds with many hits one per warp */
-template<typename F>
-__device__ __forceinline__ void af_for_each(const DevIndex &di, int n_m, const uint64_t *sv, const uint32_t *sn, const uint32_t *sq, const uint32_t *s_pre, F f)
-{
-	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-	for (int i = tid; i < n_m; i += AF_THREADS) {
-		const uint32_t cnt = sn[i];
-		if (cnt > 32) continue;
-		const uint64_t val = sv[i];
-		const uint32_t qp = sq[i], g0 = s_pre[i];
-		for (uint32_t k = 0; k < cnt; ++k) f(g0 + k, cnt == 1 ? val : di.pos[val + k], qp);
-	}
-	for (int i = wib; i < n_m; i += AF_THREADS / 32) {
-		const uint32_t cnt = sn[i];
-		if (cnt <= 32) continue;
-		const uint64_t val = sv[i];
-		const uint32_t qp = sq[i], g0 = s_pre[i];
-		for (uint32_t k = lane; k < cnt; k += 32) f(g0 + k, di.pos[val + k], qp);
-	}
-}
-
 __global__ void __launch_bounds__(AF_THREADS)
 anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 {
@@ -438,8 +417,8 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 		while (shift < 30 && (1 << shift) <= max_dist_x) ++shift;
 		const uint64_t *sv = c.sd_val + base;
 		const uint32_t *sn = c.sd_n + base, *sq = c.sd_qpos + base;
+		uint64_t *hits = c.hit_scratch + c.af_off[r];
 		const int n_words = (int)((n_full + 31) >> 5);
-		for (int j = tid; j < n_words; j += AF_THREADS) s_bits[j] = 0;
 		{ /* exclusive prefix of the seed occurrence counts: anchor index of a seed's first hit */
 			uint32_t carry = 0;
 			for (int i0 = 0; i0 < n_m; i0 += AF_THREADS) {
@@ -460,32 +439,70 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 				__syncthreads();
 			}
 		}
-		/* two rounds: the second one re-tests the survivors of the first with another hash, so that what a
-		 * collision kept by accident is (almost always) dropped after all */
+		/* Two rounds over the read's hits; the second re-tests the survivors of the first with another hash, so
+		 * that what a collision kept by accident is (almost always) dropped after all.  The index positions are
+		 * gathered ONCE (random 8-byte reads of di.pos are the expensive part) into hit_scratch, in anchor order,
+		 * with the seed's strand in bit 63; everything after that streams through it. */
 		uint32_t n_in = n_full;
 		for (int round = 0; round < 2; ++round) {
 			int bits = 12;
 			while (bits < AF_BIN_BITS && (1u << bits) < 8u * n_in) ++bits;
 			const uint32_t seed = round ? 0x68E31DA4u : 0u;
 			for (int j = tid; j < (1 << (bits - 5)); j += AF_THREADS) s_tab[j] = 0, s_two[j] = 0;
-			if (tid == 0) s_keep = 0;
 			__syncthreads();
-			af_for_each(di, n_m, sv, sn, sq, s_pre, [&](uint32_t g, uint64_t rr, uint32_t qp) {
-				if (round && !((s_bits[g >> 5] >> (g & 31)) & 1u)) return;
-				const uint32_t b0 = af_bin_slot(rr, (rr & 1) != (qp & 1), shift, 0, seed, bits);
-				if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
-			});
+			if (round == 0) { /* seeds with few hits one per thread, seeds with many hits one per warp */
+				for (int i = tid; i < n_m; i += AF_THREADS) {
+					const uint32_t cnt = sn[i];
+					if (cnt > 32) continue;
+					const uint64_t val = sv[i], qbit = (uint64_t)(sq[i] & 1u) << 63;
+					const uint32_t g0 = s_pre[i];
+					for (uint32_t k = 0; k < cnt; ++k) {
+						const uint64_t rr = cnt == 1 ? val : di.pos[val + k];
+						hits[g0 + k] = rr | qbit;
+						const uint32_t b0 = af_bin_slot(rr, (rr & 1) != (qbit >> 63), shift, 0, seed, bits);
+						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+					}
+				}
+				for (int i = wib; i < n_m; i += AF_THREADS / 32) {
+					const uint32_t cnt = sn[i];
+					if (cnt <= 32) continue;
+					const uint64_t val = sv[i], qbit = (uint64_t)(sq[i] & 1u) << 63;
+					const uint32_t g0 = s_pre[i];
+					for (uint32_t k = lane; k < cnt; k += 32) {
+						const uint64_t rr = di.pos[val + k];
+						hits[g0 + k] = rr | qbit;
+						const uint32_t b0 = af_bin_slot(rr, (rr & 1) != (qbit >> 63), shift, 0, seed, bits);
+						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+					}
+				}
+			} else {
+				for (uint32_t g = tid; g < n_full; g += AF_THREADS) {
+					if (!((s_bits[g >> 5] >> (g & 31)) & 1u)) continue;
+					const uint64_t w = hits[g], rr = w & 0x7fffffffffffffffULL;
+					const uint32_t b0 = af_bin_slot(rr, (rr & 1) != (w >> 63), shift, 0, seed, bits);
+					if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+				}
+			}
 			__syncthreads();
-			af_for_each(di, n_m, sv, sn, sq, s_pre, [&](uint32_t g, uint64_t rr, uint32_t qp) {
-				if (round && !((s_bits[g >> 5] >> (g & 31)) & 1u)) return;
-				const bool rev = (rr & 1) != (qp & 1);
-				const bool keep = af_keep(s_tab, s_two, af_bin_slot(rr, rev, shift, 0, seed, bits), af_bin_slot(rr, rev, shift, -1, seed, bits),
-				                          af_bin_slot(rr, rev, shift, 1, seed, bits));
-				if (keep) { if (!round) atomicOr(&s_bits[g >> 5], 1u << (g & 31)); atomicAdd(&s_keep, 1u); }
-				else if (round) atomicAnd(&s_bits[g >> 5], ~(1u << (g & 31)));
-			});
+			uint32_t kept = 0;
+			for (uint32_t g0 = (uint32_t)wib * 32; g0 < n_full; g0 += AF_THREADS) { /* a warp decides 32 consecutive anchors: one word */
+				const uint32_t g = g0 + lane;
+				bool keep = g < n_full && (round == 0 || ((s_bits[g >> 5] >> (g & 31)) & 1u));
+				if (keep) {
+					const uint64_t w = hits[g], rr = w & 0x7fffffffffffffffULL;
+					const bool rev = (rr & 1) != (w >> 63);
+					keep = af_keep(s_tab, s_two, af_bin_slot(rr, rev, shift, 0, seed, bits), af_bin_slot(rr, rev, shift, -1, seed, bits),
+					               af_bin_slot(rr, rev, shift, 1, seed, bits));
+				}
+				const uint32_t km = __ballot_sync(MMG_FULL, keep);
+				__syncwarp();
+				if (lane == 0) s_bits[g0 >> 5] = km;
+				kept += (uint32_t)__popc(km);
+			}
+			if (lane == 0) s_warp[wib] = kept;
 			__syncthreads();
-			n_in = s_keep;
+			n_in = 0;
+			for (int q = 0; q < AF_THREADS / 32; ++q) n_in += s_warp[q];
 			__syncthreads();
 		}
 		uint32_t *bits_out = c.keep_bits + (c.af_off[r] >> 5) + r;
