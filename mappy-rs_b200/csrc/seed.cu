@@ -356,6 +356,12 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 #define AF_MAX_SEEDS 3072
 #define AF_MAX_ANCHORS 65536
 #define AF_MIN_ANCHORS 512
+#define AF_BIG 256              /* listed high-occurrence seeds per read */
+#ifdef MMG_EMU
+#define AF_WARP_SEED 4          /* the CPU test-suite sends seeds with > 4 hits down the per-warp path so that it is exercised */
+#else
+#define AF_WARP_SEED 32         /* seeds with more hits are gathered by a whole warp */
+#endif
 
 /* hashed slot of the position bin (strand, contig, (pos >> shift) + delta) in a table of 2^bits bins */
 __device__ __forceinline__ uint32_t af_bin_slot(uint64_t rr, bool rev, int shift, int delta, uint32_t seed, int bits)
@@ -377,7 +383,7 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 {
 	MMG_DYN_SMEM(smem_raw);
 	uint32_t *s_tab = (uint32_t*)smem_raw, *s_two = s_tab + AF_TAB, *s_pre = s_two + AF_TAB, *s_bits = s_pre + AF_MAX_SEEDS + 1;
-	__shared__ uint32_t s_item, s_dup, s_keep, s_warp[AF_THREADS / 32];
+	__shared__ uint32_t s_item, s_dup, s_keep, s_nbig, s_warp[AF_THREADS / 32], s_big[AF_BIG];
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	unsigned long long dropped = 0;
 	for (;;) {
@@ -450,10 +456,12 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 			const uint32_t seed = round ? 0x68E31DA4u : 0u;
 			for (int j = tid; j < (1 << (bits - 5)); j += AF_THREADS) s_tab[j] = 0, s_two[j] = 0;
 			__syncthreads();
-			if (round == 0) { /* seeds with few hits one per thread, seeds with many hits one per warp */
+			if (round == 0) { /* seeds with few hits one per thread; seeds with many hits are listed and taken one per warp */
+				if (tid == 0) s_nbig = 0;
+				__syncthreads();
 				for (int i = tid; i < n_m; i += AF_THREADS) {
 					const uint32_t cnt = sn[i];
-					if (cnt > 32) continue;
+					if (cnt > AF_WARP_SEED) { const uint32_t q = atomicAdd(&s_nbig, 1u); if (q < AF_BIG) s_big[q] = (uint32_t)i; continue; }
 					const uint64_t val = sv[i], qbit = (uint64_t)(sq[i] & 1u) << 63;
 					const uint32_t g0 = s_pre[i];
 					for (uint32_t k = 0; k < cnt; ++k) {
@@ -463,9 +471,15 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
 					}
 				}
-				for (int i = wib; i < n_m; i += AF_THREADS / 32) {
-					const uint32_t cnt = sn[i];
-					if (cnt <= 32) continue;
+				__syncthreads();
+				const uint32_t n_big = s_nbig;
+#ifdef MMG_EMU
+				if (tid == 0 && n_big && getenv("MMG_AF_DEBUG")) fprintf(stderr, "[af] read %u: %u seeds with more than AF_WARP_SEED hits\n", r, n_big);
+#endif
+				const bool listed = n_big <= AF_BIG; /* otherwise every warp scans the seeds for its share */
+				for (uint32_t q = wib; q < (listed ? n_big : (uint32_t)n_m); q += AF_THREADS / 32) {
+					const uint32_t i = listed ? s_big[q] : q, cnt = sn[i];
+					if (cnt <= AF_WARP_SEED) continue;
 					const uint64_t val = sv[i], qbit = (uint64_t)(sq[i] & 1u) << 63;
 					const uint32_t g0 = s_pre[i];
 					for (uint32_t k = lane; k < cnt; k += 32) {

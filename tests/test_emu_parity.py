@@ -243,8 +243,11 @@ def test_radix_sort_pass_for_every_read(emu_lib, oracle_mod):
 
 def _random_hit_case(lib, oracle_mod, ref_len, seed):
     """Short k-mers on a large reference: most anchors of a read are random, isolated hits (what a human-scale
-    index does to 15-mers)."""
-    ref, coff, names, seqs = parity.random_reference(seed, [ref_len])
+    index does to 15-mers).  A 60-copy tandem array gives some seeds more than 32 hits (the filter's per-warp path)."""
+    ref, coff, names, _ = parity.random_reference(seed, [ref_len])
+    ref = ref.copy()
+    ref[1000000:1000000 + 60 * 180] = np.tile(ref[2000000:2000180], 60)
+    seqs = [ref.tobytes()]
     c = parity.Case.__new__(parity.Case)
     import ctypes
     from mappy_rs import _mmg
@@ -272,7 +275,8 @@ def test_isolated_anchor_filter_is_exact(emu_lib, oracle_mod):
     try:
         buf, offs, _ = data_gen.make_reads(98, ref, coff, 70, 900, 1900)   # short: few repeated 11-mer hashes per read
         b2, o2 = oracle_mod.pack_reads(_dup_reads(ref, 4, 99))             # repeated minimizers: these keep every anchor
-        buf = np.concatenate([buf, b2]); offs = np.concatenate([offs, o2[1:] + offs[-1]])
+        b3, o3 = oracle_mod.pack_reads([ref[a:a + 1500].tobytes().decode() for a in (998600, 999300, 1010200, 1010900, 2000000 - 700)])
+        buf = np.concatenate([buf, b2, b3]); offs = np.concatenate([offs, o2[1:] + offs[-1], o3[1:] + offs[-1] + o2[-1]])
         dev, stage_diffs = parity.compare_stages(c, buf, offs)
         ora = c.oracle.map_batch(buf, offs, 4)
         assert dev.stats["n_dropped"] > 0.2 * ora.stats["n_anchor"]
