@@ -110,8 +110,10 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 				try_bulk = false;
 			}
 			const uint64_t aix = ax[i], aiy = ay[i];
-			/* advance st: first j that shares the target strand and is within max_dist_x */
-			for (;;) {
+			/* advance st: first j that shares the target strand and is within max_dist_x (usually st itself still is) */
+			bool st_out;
+			{ const uint64_t xs = ax[st]; st_out = st < i && ((xs >> 32) != (aix >> 32) || aix > xs + (uint64_t)max_dist_x); }
+			while (st_out) {
 				int j = st + lane;
 				bool out = j < i && ((ax[j] >> 32) != (aix >> 32) || aix > ax[j] + (uint64_t)max_dist_x);
 				uint32_t m = __ballot_sync(MMG_FULL, out);
