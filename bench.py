@@ -228,7 +228,7 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    dev_ms, stage_ms, launches = 0.0, {}, 0
+    dev_ms, stage_ms, stage_ln, launches = 0.0, {}, {}, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for b in handles:
@@ -236,6 +236,7 @@ def run_ours(args, rank, local_rank, world):
             dev_ms += al.last_run_ms()
             for k, (ms, ln) in al.stage_times().items():
                 stage_ms[k] = stage_ms.get(k, 0.0) + ms
+                stage_ln[k] = stage_ln.get(k, 0) + ln
                 launches += ln
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -280,7 +281,9 @@ def run_ours(args, rank, local_rank, world):
     top_ms_step = stage_only.get(top, 0.0) / args.steps
     peak, how = measured_peak()
     achieved = ALGO_BYTES[top](stats) / (top_ms_step / 1e3) / 1e9 if top_ms_step > 0 else 0.0
-    traffic = load_traffic().get(top)
+    n_launch = max(1, stage_ln.get(top, 1) // args.steps)   # launches of the stage per step (one per chunk / sub-range)
+    tr = load_traffic().get(top)
+    traffic = tr["dram_bytes_per_launch"] if tr else None
     out = {
         "metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -292,7 +295,9 @@ def run_ours(args, rank, local_rank, world):
                 "mbases_per_s": world * n_bases / e2e_s / 1e6},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": "of " + how, "ms_per_step": top_ms_step,
+                     "traffic": traffic, "peak_source": "of " + how, "ms_per_step": top_ms_step, "launches_per_step": n_launch,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES[top](stats) / n_launch, "ms_per_launch": top_ms_step / n_launch,
+                     "traffic_source": (tr or {}).get("report"),
                      "note": "stage kernels are integer-issue / latency bound (DESIGN.md section 4); algorithmic bytes per BASELINE.md; achieved = bytes of all launches of the stage in a step / their summed event time"},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "counters": stats, "wall_ms_per_step": wall_ms / args.steps,

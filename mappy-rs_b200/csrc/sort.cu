@@ -288,7 +288,7 @@ radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uin
 	}
 }
 
-static int g_sort_small_max = 1024;
+static int g_sort_small_max = 512;
 void mmg_sort_set_small_max(int v) { g_sort_small_max = v < 0 ? 0 : v > SORT_SMALL_ELEMS ? SORT_SMALL_ELEMS : v; }
 
 int launch_sort(const ChunkDev &c, const DevIndex &di, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work)

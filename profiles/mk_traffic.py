@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """dram bytes per launch of every stage kernel from an `ncu --set full` report -> profiles/traffic.json
-(read by bench.py for roofline.traffic).  usage: mk_traffic.py report.ncu-rep [workload tag]"""
+(read by bench.py for roofline.traffic).  usage: mk_traffic.py report.ncu-rep [workload tag] [stage launches covered by the capture]"""
 import collections, csv, json, os, subprocess, sys
 
 STAGE = [("sketch_kernel", "sketch"), ("seed_kernel", "seed"), ("anchor_filter_kernel", "expand"), ("expand_kernel", "expand"),
@@ -25,8 +25,9 @@ def main():
         per[st][0] += 1
         per[st][1] += b
         per[st][2] += float(r[du].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[du], 1.0)
-    out = {st: {"dram_bytes_per_chunk": v[1], "kernel_launches_captured": v[0], "ms_under_ncu": v[2], "report": os.path.basename(rep), "workload": tag}
-           for st, v in per.items()}
+    n_chunks = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # stage launches (chunks) the capture covers
+    out = {st: {"dram_bytes_per_launch": v[1] / n_chunks, "kernels_captured": v[0], "stage_launches_captured": n_chunks, "ms_under_ncu_per_launch": v[2] / n_chunks,
+                "report": os.path.basename(rep), "workload": tag} for st, v in per.items()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print(json.dumps(out, indent=1, sort_keys=True))

@@ -224,7 +224,7 @@ def test_equal_anchor_keys_replay_upstream_order(emu_lib, oracle_mod):
 
 
 def test_radix_sort_pass_for_every_read(emu_lib, oracle_mod):
-    """sort_small_max = 0 sends every read through the CTA radix sort (the path of reads with > 1024 anchors),
+    """sort_small_max = 0 sends every read through the CTA radix sort (the path of reads with > 512 anchors),
     including its equal-key replay; two contigs so that the linear target coordinate spans contigs."""
     ref, coff, names, seqs = parity.random_reference(93, [90000, 50000])
     c = parity.Case(emu_lib, names, seqs)
@@ -237,7 +237,7 @@ def test_radix_sort_pass_for_every_read(emu_lib, oracle_mod):
         ora = c.oracle.map_batch(buf, offs, 4)
         assert stage_diffs == [] and parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
     finally:
-        c.aligner.set("sort_small_max", 1024)
+        c.aligner.set("sort_small_max", 512)
         c.close()
 
 
