@@ -538,10 +538,26 @@ __device__ __forceinline__ bool ez_apply_zdrop(int32_t *ez_max, int *ez_max_t, i
 	return false;
 }
 
-/* One pass of ksw_extd2_sse over (qlen x tlen).  All lanes of the warp call it. */
-__device__ void ext_dp_pass(const DpMem &m, const DevOpt &o, int qlen, int tlen, int w, int zdrop, int end_bonus, int flag,
-                            uint8_t *tb, uint32_t *cigar, ExtJob *res, unsigned long long *n_cell)
+__device__ __forceinline__ void ext_dpmem_set(DpMem &m, unsigned char *base, int T16, int Q16)
 {
+	m.T16 = T16, m.flat_sz = T16 + Q16 + 16;
+	m.H = (int32_t*)base;
+	m.u = (int8_t*)(base + (size_t)4 * T16), m.v = m.u + T16, m.x = m.v + T16, m.y = m.x + T16, m.x2 = m.y + T16, m.y2 = m.x2 + T16, m.s = m.y2 + T16;
+	m.sf = (uint8_t*)(m.s + T16);
+}
+
+/* One pass of ksw_extd2_sse over (qlen x tlen).  All lanes of the warp call it.  SMEM = true: the job's arrays are
+ * the warp's shared-memory slice; the pointers are derived from the shared array inside this function so that the
+ * compiler emits shared-memory loads/stores with 32-bit addresses instead of generic ones. */
+template<bool SMEM>
+__device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q16, const DevOpt &o, int qlen, int tlen, int w, int zdrop, int end_bonus, int flag,
+                                           uint8_t *tb, uint32_t *cigar, ExtJob *res, unsigned long long *n_cell)
+{
+	DpMem m;
+	if (SMEM) {
+		MMG_DYN_SMEM(dp_smem);
+		ext_dpmem_set(m, dp_smem + (size_t)(threadIdx.x >> 5) * EXT_SMEM_PER_WARP, T16, Q16);
+	} else ext_dpmem_set(m, gbase, T16, Q16);
 	const int lane = mmg_lane();
 	int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
 	if (q2 + e2 < q + e) { int t = q; q = q2, q2 = t, t = e, e = e2, e2 = t; }
@@ -552,7 +568,7 @@ __device__ void ext_dp_pass(const DpMem &m, const DevOpt &o, int qlen, int tlen,
 	if (w < 0) w = tlen > qlen ? tlen : qlen;
 	int n_col_ = qlen < tlen ? qlen : tlen;
 	n_col_ = ((n_col_ < w + 1 ? n_col_ : w + 1) + 15) / 16 + 1;
-	const int n_col = n_col_ * 16, T16 = m.T16;
+	const int n_col = n_col_ * 16;
 	int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
 	if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
 	const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
@@ -784,6 +800,13 @@ __device__ void ext_dp_pass(const DpMem &m, const DevOpt &o, int qlen, int tlen,
 	__syncwarp();
 }
 
+__device__ __forceinline__ void ext_dp_pass(bool in_smem, unsigned char *gbase, int T16, int Q16, const DevOpt &o, int qlen, int tlen, int w, int zdrop, int end_bonus,
+                                            int flag, uint8_t *tb, uint32_t *cigar, ExtJob *res, unsigned long long *n_cell)
+{
+	if (in_smem) ext_dp_pass_t<true>(gbase, T16, Q16, o, qlen, tlen, w, zdrop, end_bonus, flag, tb, cigar, res, n_cell);
+	else ext_dp_pass_t<false>(gbase, T16, Q16, o, qlen, tlen, w, zdrop, end_bonus, flag, tb, cigar, res, n_cell);
+}
+
 /* align.c mm_test_zdrop without the inversion test (lane 0); returns max_zdrop and the most-dropped region */
 __device__ int ext_test_zdrop(const DpMem &m, const DevOpt &o, int qlen, int n_cigar, const uint32_t *cigar, int pos[2][2])
 {
@@ -905,10 +928,8 @@ ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint32
 			__syncwarp();
 			continue;
 		}
-		m.T16 = T16, m.flat_sz = T16 + Q16 + 16;
-		m.H = (int32_t*)base;
-		m.u = (int8_t*)(base + (size_t)4 * T16), m.v = m.u + T16, m.x = m.v + T16, m.y = m.x + T16, m.x2 = m.y + T16, m.y2 = m.x2 + T16, m.s = m.y2 + T16;
-		m.sf = (uint8_t*)(m.s + T16);
+		const bool in_smem = need <= EXT_SMEM_PER_WARP;
+		ext_dpmem_set(m, base, T16, Q16);
 		/* load the sequences: target codes, reversed query codes, zero padding */
 		const uint64_t toff = di.seq_off[jb->rid];
 		const bool is_left = jb->kind == EXT_LEFT;
@@ -927,7 +948,7 @@ ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint32
 			__syncwarp();
 			continue;
 		}
-		ext_dp_pass(m, o, qlen, tlen, jb->w, jb->zdrop, jb->end_bonus, flag, tb, cigar, jb, &n_cell);
+		ext_dp_pass(in_smem, base, T16, Q16, o, qlen, tlen, jb->w, jb->zdrop, jb->end_bonus, flag, tb, cigar, jb, &n_cell);
 		if (jb->kind == EXT_FILL) {
 			/* mm_test_zdrop on the first-pass CIGAR; a second, exact pass when the score drops too much */
 			int code = 0, pos[2][2];
@@ -951,7 +972,7 @@ ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint32
 					code = mz > o.zdrop ? 1 : 0;
 				}
 			}
-			if (code != 0) ext_dp_pass(m, o, qlen, tlen, jb->w, code == 2 ? o.zdrop_inv : o.zdrop, -1, 0, tb, cigar, jb, &n_cell);
+			if (code != 0) ext_dp_pass(in_smem, base, T16, Q16, o, qlen, tlen, jb->w, code == 2 ? o.zdrop_inv : o.zdrop, -1, 0, tb, cigar, jb, &n_cell);
 			if (lane == 0) jb->zdrop_code = (uint8_t)code;
 		}
 		__syncwarp();
