@@ -507,7 +507,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	/* isolated-anchor filter (exact under these conditions, see seed.cu): worth its two passes over the hits only
 	 * when reads carry many anchors, i.e. on large references */
 	if (al->anchor_filter && al->mo.min_cnt >= 2 && al->mo.min_chain_score > al->idx->k && c.n_reads > 0 &&
-	    a_total > (uint64_t)c.n_reads * 512 && (a_total >> 5) + c.n_reads + 1 <= al->cap_keep_words) {
+	    a_total > (uint64_t)c.n_reads * 64 && (a_total >> 5) + c.n_reads + 1 <= al->cap_keep_words) {
 		STAGE_BEGIN();
 		CK(cudaMemcpyAsync(c.af_off, c.a_off, (size_t)(c.n_reads + 1) * 8, cudaMemcpyDeviceToDevice, st));
 		launch_anchor_filter(c, al->di, al->dopt, al->n_sms, st, work + wi++);

@@ -355,7 +355,7 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 #define AF_BIN_BITS 17
 #define AF_MAX_SEEDS 3072
 #define AF_MAX_ANCHORS 65536
-#define AF_MIN_ANCHORS 512
+#define AF_MIN_ANCHORS 64
 #define AF_BIG 256              /* listed high-occurrence seeds per read */
 #ifdef MMG_EMU
 #define AF_WARP_SEED 4          /* the CPU test-suite sends seeds with > 4 hits down the per-warp path so that it is exercised */
@@ -393,7 +393,8 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 		if (r >= c.n_reads) break;
 		const uint32_t n_full = c.n_a[r];
 		const int n_m = (int)c.n_seed[r], n_mz = (int)c.n_mz[r];
-		if (n_full < AF_MIN_ANCHORS || n_full > AF_MAX_ANCHORS || n_m > AF_MAX_SEEDS || n_mz > AF_MAX_SEEDS) { __syncthreads(); continue; }
+		/* worth it only where the index returns several hits per seed (large references): most of them are random */
+		if (n_full < AF_MIN_ANCHORS || n_full < 2u * (uint32_t)n_m || n_full > AF_MAX_ANCHORS || n_m > AF_MAX_SEEDS || n_mz > AF_MAX_SEEDS) { __syncthreads(); continue; }
 		const uint64_t base = c.off[r] - c.off0;
 		const int qlen = (int)(c.off[r + 1] - c.off[r]);
 		/* (0) a minimizer hash that occurs twice in the read?  open-addressing set of 32-bit fingerprints */
