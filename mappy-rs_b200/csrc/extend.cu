@@ -893,7 +893,7 @@ __device__ int ext_inv_score(const DpMem &m, const DevOpt &o, int qlen, int pos[
 	return gmax > 32767 ? 32767 : gmax;
 }
 
-__global__ void __launch_bounds__(EXT_DP_WARPS * 32, 6)
+__global__ void __launch_bounds__(EXT_DP_WARPS * 32)
 ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint32_t j1, uint32_t *work)
 {
 	MMG_DYN_SMEM(smem_raw);

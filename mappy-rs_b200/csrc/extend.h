@@ -4,7 +4,7 @@
 #include "dev_common.cuh"
 
 #define EXT_DP_WARPS 4
-#define EXT_SMEM_PER_WARP 8192    /* bytes of shared memory per DP warp: jobs up to ~600 x 600 bases; 6 CTAs of 4 warps per SM */
+#define EXT_SMEM_PER_WARP 12288   /* bytes of shared memory per DP warp: jobs up to ~900 x 900 bases */
 #define EXT_LEFT 0
 #define EXT_FILL 1
 #define EXT_RIGHT 2
