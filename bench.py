@@ -192,6 +192,8 @@ def run_ours(args, rank, local_rank, world):
     lib.check(lib.L.mmg_mapopt_update(ctypes.byref(mopt), idx.h))
     al = _mmg.DeviceAligner(lib, idx, mopt, device=local_rank)
     al.set("profile", 1)
+    if os.environ.get("MMG_RAMP_SHIFT"):
+        al.set("ramp_shift", int(os.environ["MMG_RAMP_SHIFT"]))
     if os.environ.get("MMG_SORT_SMALL_MAX"):
         al.set("sort_small_max", int(os.environ["MMG_SORT_SMALL_MAX"]))
     # pinned host staging (torch is plumbing here: pinned memory + process group)

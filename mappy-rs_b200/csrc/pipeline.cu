@@ -32,6 +32,7 @@ struct mmg_aligner {
 	std::vector<void*> dev_allocs;     /* index + arenas */
 	/* arena capacities */
 	uint64_t cap_bases, cap_anchors, cap_regs, cap_keep_words;
+	int ramp_shift;                    /* streamed mode: the first chunk is 1/2^ramp_shift of the arena (tuning knob "ramp_shift") */
 	int anchor_filter;                 /* 1 = drop isolated anchors before the sort (seed.cu anchor_filter_kernel) */
 	uint32_t cap_reads;
 	bool arenas_ready;
@@ -231,6 +232,7 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 		al->cap_keep_words = (uint64_t)1 << 24;
 	}
 	al->anchor_filter = 1;
+	al->ramp_shift = 2;
 	al->cap_tb = (uint64_t)32 << 30, al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48, al->big_per_warp = (uint64_t)1 << 20;
 	memset(&al->xb, 0, sizeof(al->xb));
 	al->cg_read_off = 0;
@@ -278,6 +280,7 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 	if (strcmp(key, "profile") == 0) { al->profile = (int)v; return MMG_OK; }
 	if (strcmp(key, "sort_small_max") == 0) { mmg_sort_set_small_max((int)v); return MMG_OK; }
 	if (strcmp(key, "anchor_filter") == 0) { al->anchor_filter = v != 0; return MMG_OK; }
+	if (strcmp(key, "ramp_shift") == 0) { al->ramp_shift = v < 0 ? 0 : v > 6 ? 6 : (int)v; return MMG_OK; }
 	if (al->arenas_ready) { mmg_set_error("arena sizes are fixed after the first batch"); return MMG_EINVAL; }
 	if (strcmp(key, "chunk_bases") == 0) al->cap_bases = (uint64_t)v;
 	else if (strcmp(key, "chunk_reads") == 0) al->cap_reads = (uint32_t)v;
@@ -601,14 +604,14 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	return MMG_OK;
 }
 
-/* ramp: streamed mode starts with small chunks (1/8, 1/4, 1/2 of the arena) so that the first kernels start after
+/* ramp: streamed mode starts with a small chunk (1/4 of the arena by default) so that the first kernels start after
  * a short copy-in and the copy of every later chunk hides behind the compute of its predecessor */
 static void cut_chunks(const mmg_aligner *al, const mmg_batch *b, std::vector<uint32_t> &cuts, bool ramp)
 {
 	const uint32_t n = b->n_reads;
 	cuts.clear();
 	cuts.push_back(0);
-	int shift = ramp ? 3 : 0;
+	int shift = ramp ? al->ramp_shift : 0;
 	for (uint32_t r0 = 0; r0 < n;) {
 		uint32_t r1 = r0;
 		const uint64_t cap = al->cap_bases >> shift;
@@ -618,7 +621,7 @@ static void cut_chunks(const mmg_aligner *al, const mmg_batch *b, std::vector<ui
 		}
 		cuts.push_back(r1);
 		r0 = r1;
-		if (shift > 0) --shift;
+		shift = shift > 2 ? shift - 1 : 0; /* 1/8, 1/4, then full chunks */
 	}
 }
 

@@ -234,7 +234,7 @@ static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64
  * (key, source index) staged in shared memory (the cycle-leader permutation is a chain of dependent accesses: the
  * latency of shared memory instead of L2), the stable leaf insertion sorts are replaced by a second radix sort on
  * (key, position after those passes) - see the tie path of sort_kernel. */
-#define RSORT_TIE_TILE 8192
+#define RSORT_TIE_TILE 16384      /* records staged in shared memory by the equal-key replay (192 KB: one CTA per SM; these reads are rare) */
 template<bool TIE>
 __global__ void __launch_bounds__(RSORT_WARPS * 32)
 radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uint32_t *list, const uint32_t *n_list, uint32_t *tie_list, uint32_t *n_tie)
