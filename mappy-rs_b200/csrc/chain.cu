@@ -67,6 +67,7 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 	for (;;) {
 		uint32_t r = r0 + mmg_next_item(work);
 		if (r >= r1) break;
+		r = mmg_read_of(c, r);
 		const int n = (int)c.n_a[r];
 		const uint64_t ab = c.a_off[r] - c.a_off0;
 		const int qlen = (int)(c.off[r + 1] - c.off[r]);
@@ -235,6 +236,7 @@ backtrack_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 	for (;;) {
 		uint32_t r = r0 + mmg_next_item(work);
 		if (r >= r1) break;
+		r = mmg_read_of(c, r);
 		const int n = (int)c.n_a[r];
 		const uint64_t ab = c.a_off[r] - c.a_off0;
 		int n_u = 0, n_v = 0;

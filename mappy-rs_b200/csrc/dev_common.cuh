@@ -85,6 +85,8 @@ struct ChunkDev {
 	const char *seq;          /* concatenated ASCII bases */
 	const uint64_t *off;      /* n_reads + 1: absolute offsets into seq */
 	uint64_t off0;            /* off[0]: per-read slices of the base-sized arrays start at off[r] - off0 */
+	const uint32_t *order;    /* work order of the reads of the chunk, longest first (0 = index order): every per-read kernel claims
+	                           * item i and works on read order[i], so that a launch does not end with its longest reads */
 	const uint64_t *seg_beg;  /* segment mode of the sketch kernel (index construction), else 0 */
 	const uint32_t *seg_len;
 	uint32_t seg_cap;
@@ -127,6 +129,8 @@ __device__ __forceinline__ uint32_t mmg_next_item(uint32_t *counter)
 	if (mmg_lane() == 0) r = atomicAdd(counter, 1u);
 	return __shfl_sync(MMG_FULL, r, 0);
 }
+
+__device__ __forceinline__ uint32_t mmg_read_of(const ChunkDev &c, uint32_t item) { return c.order ? c.order[item] : item; }
 
 __device__ __forceinline__ int mmg_warp_excl_scan(int v, int *total)
 {

@@ -342,6 +342,7 @@ ext_prep_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t r0, uint
 	for (;;) {
 		uint32_t r = r0 + mmg_next_item(work);
 		if (r >= r1) break;
+		r = mmg_read_of(c, r);
 		const int n_regs = (int)c.n_regs[r];
 		if (n_regs == 0) continue;
 		const uint64_t ab = c.a_off[r] - c.a_off0, rb = xb.xr_off[r];

@@ -38,6 +38,8 @@ struct mmg_aligner {
 	bool arenas_ready;
 	ChunkDev cd;                       /* arena pointers */
 	unsigned char *rmq_nodes;          /* AVL node arena of the re-chain stage */
+	uint32_t *d_order;                 /* longest-first work order of the chunk's reads */
+	std::vector<uint32_t> h_order, h_bins;
 	ExtBufs xb;                        /* extension stage arenas (allocated when MM_F_CIGAR is set) */
 	uint64_t *cg_read_off;
 	uint64_t cap_tb, cap_cg, cap_jobs, big_per_warp;
@@ -166,7 +168,7 @@ static int alloc_arenas(mmg_aligner *al)
 	AL(c.n_u, R); AL(c.n_v, R); AL(c.r_off, R + 1);
 	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
 	AL(c.work, 64); AL(c.flags, R); AL(c.big_list, R); AL(c.tie_list, R);
-	AL(c.af_off, R + 1); AL(c.keep_bits, al->cap_keep_words); AL(c.hit_scratch, al->cap_keep_words * 32);
+	AL(al->d_order, R); AL(c.af_off, R + 1); AL(c.keep_bits, al->cap_keep_words); AL(c.hit_scratch, al->cap_keep_words * 32);
 	AL(al->rmq_nodes, (2 * A + 2 * R + 2) * RMQ_NODE_BYTES);
 	if (al->mo.flag & MMG_F_CIGAR) {
 		ExtBufs &x = al->xb;
@@ -232,7 +234,7 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 		al->cap_keep_words = (uint64_t)1 << 24;
 	}
 	al->anchor_filter = 1;
-	al->ramp_shift = 2;
+	al->ramp_shift = 1;
 	al->cap_tb = (uint64_t)32 << 30, al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48, al->big_per_warp = (uint64_t)1 << 20;
 	memset(&al->xb, 0, sizeof(al->xb));
 	al->cg_read_off = 0;
@@ -501,6 +503,24 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	int wi = 0;
 	CK(cudaMemsetAsync(c.work, 0, 64 * 4, st));
 	CK(cudaMemsetAsync(c.flags, 0, (size_t)c.n_reads * 4, st));
+	{ /* work order: reads by descending length (counting sort on length / 64), so that a kernel's persistent warps take
+	   * the long reads first and the launch does not end with a few of them still running */
+		const uint32_t n = c.n_reads;
+		std::vector<uint32_t> &ord = al->h_order, &bins = al->h_bins;
+		ord.resize(n);
+		bins.assign(4097, 0);
+		for (uint32_t i = 0; i < n; ++i) {
+			uint64_t l = (b->off[r0 + i + 1] - b->off[r0 + i]) >> 6;
+			++bins[4095 - (l > 4095 ? 4095 : (uint32_t)l) + 1];
+		}
+		for (int k = 1; k <= 4096; ++k) bins[k] += bins[k - 1];
+		for (uint32_t i = 0; i < n; ++i) {
+			uint64_t l = (b->off[r0 + i + 1] - b->off[r0 + i]) >> 6;
+			ord[bins[4095 - (l > 4095 ? 4095 : (uint32_t)l)]++] = i;
+		}
+		if (n) CK(cudaMemcpyAsync(al->d_order, ord.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+		c.order = al->d_order;
+	}
 	STAGE_BEGIN(); launch_sketch(c, al->di, al->n_sms, st, work + wi++); STAGE_END(ST_SKETCH);
 	STAGE_BEGIN(); launch_seed(c, al->di, al->dopt, al->n_sms, st, work + wi++); STAGE_END(ST_SEED);
 	STAGE_BEGIN(); launch_scan_u32(c.n_a, c.a_off, c.n_reads, st); STAGE_END(ST_SCAN);
@@ -520,6 +540,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 		CK(cudaStreamSynchronize(st));
 	}
 	const bool split = a_total > al->cap_anchors;
+	if (split) c.order = 0; /* the order is a permutation of the whole chunk, not of a sub-range */
 	if (split) { /* the per-read offsets are only needed to cut sub-ranges */
 		h_aoff.resize(c.n_reads + 1);
 		CK(cudaMemcpyAsync(h_aoff.data(), c.a_off, (size_t)(c.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -604,7 +625,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	return MMG_OK;
 }
 
-/* ramp: streamed mode starts with a small chunk (1/4 of the arena by default) so that the first kernels start after
+/* ramp: streamed mode starts with a smaller chunk (1/2 of the arena by default) so that the first kernels start after
  * a short copy-in and the copy of every later chunk hides behind the compute of its predecessor */
 static void cut_chunks(const mmg_aligner *al, const mmg_batch *b, std::vector<uint32_t> &cuts, bool ramp)
 {

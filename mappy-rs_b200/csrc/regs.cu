@@ -28,6 +28,7 @@ regs_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint64_
 	for (;;) {
 		uint32_t r = r0 + mmg_next_item(work);
 		if (r >= r1) break;
+		r = mmg_read_of(c, r);
 		const int n_u = (int)c.n_u[r];
 		const uint64_t ab = c.a_off[r] - c.a_off0, rb = c.r_off[r];
 		const int qlen = (int)(c.off[r + 1] - c.off[r]);

@@ -399,6 +399,7 @@ rechain_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, uin
 	for (;;) {
 		uint32_t r = r0 + mmg_next_item(work);
 		if (r >= r1) break;
+		r = mmg_read_of(c, r);
 		int n_u = (int)c.n_u[r];
 		if (!(o.bw_long > o.bw && !(o.flag & MMG_F_NO_LJOIN) && n_u > 1)) continue;
 		const uint64_t ab = c.a_off[r] - c.a_off0;

@@ -118,6 +118,7 @@ seed_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 	for (;;) {
 		uint32_t r = mmg_next_item(work);
 		if (r >= c.n_reads) break;
+		r = mmg_read_of(c, r);
 		const uint64_t base = c.off[r] - c.off0;
 		const int qlen = (int)(c.off[r + 1] - c.off[r]);
 		int n = (int)c.n_mz[r];
@@ -275,6 +276,7 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 	for (;;) {
 		uint32_t r = r0 + mmg_next_item(work);
 		if (r >= r1) break;
+		r = mmg_read_of(c, r);
 		const uint64_t base = c.off[r] - c.off0;
 		const int qlen = (int)(c.off[r + 1] - c.off[r]);
 		const int n_m = (int)c.n_seed[r];
@@ -389,8 +391,8 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 	for (;;) {
 		if (tid == 0) s_item = atomicAdd(work, 1u), s_dup = 0, s_keep = 0;
 		__syncthreads();
-		const uint32_t r = s_item;
-		if (r >= c.n_reads) break;
+		if (s_item >= c.n_reads) break;
+		const uint32_t r = mmg_read_of(c, s_item);
 		const uint32_t n_full = c.n_a[r];
 		const int n_m = (int)c.n_seed[r], n_mz = (int)c.n_mz[r];
 		/* worth it only where the index returns several hits per seed (large references): most of them are random */

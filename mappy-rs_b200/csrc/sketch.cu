@@ -113,6 +113,7 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 	for (;;) {
 		uint32_t r = mmg_next_item(work);
 		if (r >= c.n_reads) break;
+		r = mmg_read_of(c, r);
 		uint64_t base;
 		int len;
 		const char *s;

@@ -47,7 +47,7 @@ sort_kernel(ChunkDev c, uint32_t r0, uint32_t r1, uint32_t *work, uint32_t *big_
 		if (tid == 0) s_item = atomicAdd(work, 1u), s_tie = 0;
 		__syncthreads();
 		if (s_item >= n_items) break;
-		const uint32_t r = LIST ? big_list[s_item] : r0 + s_item;
+		const uint32_t r = LIST ? big_list[s_item] : mmg_read_of(c, r0 + s_item);
 		const int n = (int)c.n_a[r];
 		if (!LIST && n > small_max) { /* uniform over the CTA */
 			if (tid == 0) big_list[atomicAdd(n_big, 1u)] = r;
