@@ -39,7 +39,6 @@ struct mmg_aligner {
 	ChunkDev cd;                       /* arena pointers */
 	unsigned char *rmq_nodes;          /* AVL node arena of the re-chain stage */
 	uint32_t *d_order;                 /* longest-first work order of the chunk's reads */
-	std::vector<uint32_t> h_order, h_bins;
 	ExtBufs xb;                        /* extension stage arenas (allocated when MM_F_CIGAR is set) */
 	uint64_t *cg_read_off;
 	uint64_t cap_tb, cap_cg, cap_jobs, big_per_warp;
@@ -183,6 +182,37 @@ static int alloc_arenas(mmg_aligner *al)
 #undef AL
 	al->arenas_ready = true;
 	return MMG_OK;
+}
+
+/* counting sort of the chunk's reads by length / 64, longest first (one CTA; ties in any order) */
+__global__ void __launch_bounds__(1024)
+read_order_kernel(const uint64_t *off, uint32_t n, uint32_t *order)
+{
+	__shared__ uint32_t s_bin[4096];
+	const uint32_t tid = threadIdx.x;
+	for (uint32_t k = tid; k < 4096; k += 1024) s_bin[k] = 0;
+	__syncthreads();
+	for (uint32_t i = tid; i < n; i += 1024) {
+		const uint64_t l = (off[i + 1] - off[i]) >> 6;
+		atomicAdd(&s_bin[4095 - (l > 4095 ? 4095u : (uint32_t)l)], 1u);
+	}
+	__syncthreads();
+	if (tid < 32) { /* exclusive prefix over the 4096 bins: 128 consecutive bins per lane */
+		uint32_t sum = 0;
+		for (uint32_t k = 0; k < 128; ++k) sum += s_bin[tid * 128 + k];
+		uint32_t x = sum;
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t y = __shfl_up_sync(MMG_FULL, x, d);
+			if ((int)tid >= d) x += y;
+		}
+		uint32_t run = x - sum;
+		for (uint32_t k = 0; k < 128; ++k) { const uint32_t v = s_bin[tid * 128 + k]; s_bin[tid * 128 + k] = run; run += v; }
+	}
+	__syncthreads();
+	for (uint32_t i = tid; i < n; i += 1024) {
+		const uint64_t l = (off[i + 1] - off[i]) >> 6;
+		order[atomicAdd(&s_bin[4095 - (l > 4095 ? 4095u : (uint32_t)l)], 1u)] = i;
+	}
 }
 
 __global__ void reg_cap_kernel(const uint32_t *n_u, uint32_t *cap, uint32_t n)
@@ -503,24 +533,11 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	int wi = 0;
 	CK(cudaMemsetAsync(c.work, 0, 64 * 4, st));
 	CK(cudaMemsetAsync(c.flags, 0, (size_t)c.n_reads * 4, st));
-	{ /* work order: reads by descending length (counting sort on length / 64), so that a kernel's persistent warps take
-	   * the long reads first and the launch does not end with a few of them still running */
-		const uint32_t n = c.n_reads;
-		std::vector<uint32_t> &ord = al->h_order, &bins = al->h_bins;
-		ord.resize(n);
-		bins.assign(4097, 0);
-		for (uint32_t i = 0; i < n; ++i) {
-			uint64_t l = (b->off[r0 + i + 1] - b->off[r0 + i]) >> 6;
-			++bins[4095 - (l > 4095 ? 4095 : (uint32_t)l) + 1];
-		}
-		for (int k = 1; k <= 4096; ++k) bins[k] += bins[k - 1];
-		for (uint32_t i = 0; i < n; ++i) {
-			uint64_t l = (b->off[r0 + i + 1] - b->off[r0 + i]) >> 6;
-			ord[bins[4095 - (l > 4095 ? 4095 : (uint32_t)l)]++] = i;
-		}
-		if (n) CK(cudaMemcpyAsync(al->d_order, ord.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-		c.order = al->d_order;
-	}
+	/* work order: reads by descending length, so that a kernel's persistent warps take the long reads first and the
+	 * launch does not end with a few of them still running (computed on the device: a host-side table would have to
+	 * queue behind the next chunk's input on the copy engine) */
+	if (c.n_reads) MMG_LAUNCH(read_order_kernel, 1, 1024, 0, st, c.off, c.n_reads, al->d_order);
+	c.order = al->d_order;
 	STAGE_BEGIN(); launch_sketch(c, al->di, al->n_sms, st, work + wi++); STAGE_END(ST_SKETCH);
 	STAGE_BEGIN(); launch_seed(c, al->di, al->dopt, al->n_sms, st, work + wi++); STAGE_END(ST_SEED);
 	STAGE_BEGIN(); launch_scan_u32(c.n_a, c.a_off, c.n_reads, st); STAGE_END(ST_SCAN);
