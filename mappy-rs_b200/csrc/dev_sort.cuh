@@ -198,6 +198,133 @@ static __device__ void dev_radix_sort_warp(uint64_t *x, YT *y, int n, int *bkt, 
 	}
 }
 
+/* The radix passes (no leaf sorts) called by a WHOLE CTA: the pending ranges sit on a shared stack and every warp takes
+ * one at a time, so that after the first pass (one range, one warp) the independent sub-ranges are permuted by
+ * different warps at the same time.  bkt_all: 512 ints of shared memory per warp; ctl: 3 ints {lock, stack size,
+ * ranges not finished}; stack: 3 ints per range, at least n / 65 + 1 ranges.
+ * (The SIMT emulator of the CPU test-suite runs its fibers cooperatively and cannot spin on a lock: there warp 0
+ * does all ranges through dev_radix_sort_warp.) */
+template<typename YT>
+static __device__ void dev_radix_passes_cta(uint64_t *x, YT *y, int n, int *bkt_all, int *ctl, int *stack, int *stk_global)
+{
+	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
+	const uint32_t lt = mmg_lanemask_lt();
+	if (n <= 64) return;
+#ifdef MMG_EMU
+	if (wib == 0) dev_radix_sort_warp<YT, false>(x, y, n, bkt_all, stk_global);
+	__syncthreads();
+	return;
+#else
+	(void)stk_global;
+	int *bb = bkt_all + wib * 512, *be = bb + 256;
+	for (int k = lane; k < 256; k += 32) be[k] = 0;
+	if (threadIdx.x == 0) ctl[0] = 0, ctl[1] = 1, ctl[2] = 1, stack[0] = 0, stack[1] = n, stack[2] = 56;
+	__syncthreads();
+	for (;;) {
+		int beg = 0, end = 0, s = 0, got = 0;
+		if (lane == 0) {
+			for (;;) {
+				if (*(volatile int*)&ctl[2] == 0) { got = -1; break; }
+				if (*(volatile int*)&ctl[1] > 0 && atomicCAS(&ctl[0], 0, 1) == 0) {
+					int sp = *(volatile int*)&ctl[1];
+					if (sp > 0) {
+						--sp;
+						beg = *(volatile int*)&stack[3 * sp], end = *(volatile int*)&stack[3 * sp + 1], s = *(volatile int*)&stack[3 * sp + 2];
+						*(volatile int*)&ctl[1] = sp;
+						got = 1;
+					}
+					__threadfence_block();
+					atomicExch(&ctl[0], 0);
+					if (got) break;
+				}
+			}
+		}
+		got = __shfl_sync(MMG_FULL, got, 0);
+		if (got < 0) break;
+		beg = __shfl_sync(MMG_FULL, beg, 0), end = __shfl_sync(MMG_FULL, end, 0), s = __shfl_sync(MMG_FULL, s, 0);
+		int kmin, kmax;
+		for (;;) { /* be[] is all zero here */
+			int mn = 255, mx = 0;
+			for (int i = beg + lane; i < end; i += 32) {
+				int b = (int)((x[i] >> s) & 255);
+				atomicAdd(&be[b], 1);
+				mn = b < mn ? b : mn, mx = b > mx ? b : mx;
+			}
+			kmin = __reduce_min_sync(MMG_FULL, mn), kmax = __reduce_max_sync(MMG_FULL, mx);
+			__syncwarp();
+			if (kmin != kmax || s == 0) break;
+			if (lane == 0) be[kmin] = 0;
+			__syncwarp();
+			s -= 8;
+		}
+		{
+			int carry = beg;
+			for (int k0 = kmin; k0 <= kmax; k0 += 32) {
+				const int k = k0 + lane, cnt = k <= kmax ? be[k] : 0;
+				int tot, ex = mmg_warp_excl_scan(cnt, &tot);
+				if (k <= kmax) bb[k] = carry + ex, be[k] = carry + ex + cnt;
+				carry += tot;
+			}
+		}
+		__syncwarp();
+		if (lane == 0) {
+			for (int k = kmin; k <= kmax;) {
+				if (bb[k] != be[k]) {
+					int l = (int)((x[bb[k]] >> s) & 255);
+					if (l != k) {
+						uint64_t tx = x[bb[k]];
+						YT ty = y[bb[k]];
+						do {
+							uint64_t sx = tx;
+							YT sy = ty;
+							int q = bb[l]++;
+							tx = x[q], ty = y[q];
+							x[q] = sx, y[q] = sy;
+							l = (int)((tx >> s) & 255);
+						} while (l != k);
+						x[bb[k]] = tx, y[bb[k]] = ty;
+						++bb[k];
+					} else ++bb[k];
+				} else ++k;
+			}
+		}
+		__syncwarp();
+		if (s) {
+			const int s2 = s > 8 ? s - 8 : 0;
+			for (int k0 = kmin; k0 <= kmax; k0 += 32) {
+				const int k = k0 + lane;
+				int start = 0, e = 0, sz = 0;
+				if (k <= kmax) e = be[k], start = k == kmin ? beg : be[k - 1], sz = e - start;
+				const bool push = sz > 64;
+				const uint32_t pm = __ballot_sync(MMG_FULL, push);
+				if (pm) {
+					int base = 0;
+					if (lane == 0) {
+						while (atomicCAS(&ctl[0], 0, 1) != 0) {}
+						base = *(volatile int*)&ctl[1];
+					}
+					base = __shfl_sync(MMG_FULL, base, 0);
+					if (push) { const int q = base + __popc(pm & lt); stack[3 * q] = start, stack[3 * q + 1] = e, stack[3 * q + 2] = s2; }
+					__syncwarp();
+					if (lane == 0) {
+						__threadfence_block();
+						*(volatile int*)&ctl[1] = base + __popc(pm);
+						atomicAdd(&ctl[2], __popc(pm));
+						__threadfence_block();
+						atomicExch(&ctl[0], 0);
+					}
+				}
+			}
+		}
+		__syncwarp();
+		for (int k = kmin + lane; k <= kmax; k += 32) be[k] = 0;
+		__syncwarp();
+		if (lane == 0) { __threadfence_block(); atomicSub(&ctl[2], 1); }
+	}
+	__syncthreads();
+#endif
+}
+
 static __device__ void dev_radix_sort_128x(uint64_t *x, uint64_t *y, int n, int *bkt, int *stk)
 {
 	dev_radix_sort_t<uint64_t, true>(x, y, n, bkt, stk);

@@ -234,7 +234,7 @@ static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64
  * (key, source index) staged in shared memory (the cycle-leader permutation is a chain of dependent accesses: the
  * latency of shared memory instead of L2), the stable leaf insertion sorts are replaced by a second radix sort on
  * (key, position after those passes) - see the tie path of sort_kernel. */
-#define RSORT_TIE_TILE 16384      /* records staged in shared memory by the equal-key replay (192 KB: one CTA per SM; these reads are rare) */
+#define RSORT_TIE_TILE 12288      /* records staged in shared memory by the equal-key replay (144 KB + 27 KB of per-warp buckets: one CTA per SM; these reads are rare) */
 template<bool TIE>
 __global__ void __launch_bounds__(RSORT_WARPS * 32)
 radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uint32_t *list, const uint32_t *n_list, uint32_t *tie_list, uint32_t *n_tie)
@@ -242,7 +242,8 @@ radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uin
 	MMG_DYN_SMEM(smem_raw);
 	__shared__ uint32_t s_item;
 	__shared__ int s_tie;
-	__shared__ int s_bkt[512];
+	__shared__ int s_bkt[TIE ? RSORT_WARPS * 512 : 512];
+	__shared__ int s_ctl[4], s_stack[TIE ? 3 * (RSORT_TIE_TILE / 65 + 2) : 3];
 	__shared__ uint32_t s_cnt[RSORT_WARPS * 256];
 	__shared__ uint32_t s_red[2 * RSORT_WARPS];
 	const int tid = threadIdx.x, nt = blockDim.x;
@@ -263,7 +264,8 @@ radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uin
 			uint32_t *ki = n <= RSORT_TIE_TILE ? (uint32_t*)((uint64_t*)smem_raw + RSORT_TIE_TILE) : (uint32_t*)(zx + n);
 			for (int i = tid; i < n; i += nt) kx[i] = ax[i], ki[i] = (uint32_t)i;
 			__syncthreads();
-			if (tid < 32) dev_radix_sort_warp<uint32_t, false>(kx, ki, n, s_bkt, c.f + ab);
+			if (n <= RSORT_TIE_TILE) dev_radix_passes_cta<uint32_t>(kx, ki, n, s_bkt, s_ctl, s_stack, c.f + ab); /* every warp */
+			else if (tid < 32) dev_radix_sort_warp<uint32_t, false>(kx, ki, n, s_bkt, c.f + ab);
 			__syncthreads();
 			for (int i = tid; i < n; i += nt) zy[i] = kx[i], zy[n + i] = ay[ki[i]];
 			if (tid == 0) c.flags[r] |= 1u;
