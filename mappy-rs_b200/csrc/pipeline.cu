@@ -13,6 +13,7 @@
 #include <string.h>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include "mmg_internal.h"
 #include "dev_common.cuh"
 #include "stages.h"
@@ -22,7 +23,53 @@
 
 static const char *g_stage_names[MMG_N_STAGES] = { "h2d", "sketch", "seed", "scan", "expand", "sort", "chain_dp", "backtrack", "rechain", "regs", "extend", "d2h" };
 
+/* Pinned host blocks that receive the hit records of streamed batches directly (no staging copy, no page faults on a
+ * fresh allocation); a block goes back to the pool when its batch is destroyed.  Reference-counted so that a batch
+ * may outlive the aligner. */
+struct HostPool {
+	std::mutex mu;
+	std::vector<std::pair<void*, uint64_t> > blocks; /* (pointer, bytes) */
+	bool dead;
+	int refs;
+	HostPool() : dead(false), refs(1) {}
+};
+
+static void *pool_acquire(HostPool *hp, uint64_t bytes, uint64_t *got)
+{
+	{
+		std::lock_guard<std::mutex> g(hp->mu);
+		int best = -1;
+		for (size_t i = 0; i < hp->blocks.size(); ++i)
+			if (hp->blocks[i].second >= bytes && (best < 0 || hp->blocks[i].second < hp->blocks[best].second)) best = (int)i;
+		++hp->refs;
+		if (best >= 0) {
+			void *p = hp->blocks[best].first;
+			*got = hp->blocks[best].second;
+			hp->blocks.erase(hp->blocks.begin() + best);
+			return p;
+		}
+	}
+	void *p = 0;
+	bytes += bytes >> 2;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess) { std::lock_guard<std::mutex> g(hp->mu); --hp->refs; return 0; }
+	*got = bytes;
+	return p;
+}
+
+static void pool_release(HostPool *hp, void *p, uint64_t bytes)
+{
+	bool del = false;
+	{
+		std::lock_guard<std::mutex> g(hp->mu);
+		if (hp->dead) cudaFreeHost(p);
+		else hp->blocks.push_back(std::make_pair(p, bytes));
+		del = --hp->refs == 0;
+	}
+	if (del) delete hp;
+}
+
 struct mmg_aligner {
+	HostPool *pool;
 	const mmg_index *idx;
 	mmg_mapopt_t mo;
 	int device, n_sms;
@@ -86,6 +133,7 @@ struct mmg_batch {
 	uint64_t stats[MMG_N_STATS];
 	bool uploaded, ran, fetched;
 	bool streamed;                     /* inputs/results go through the aligner's streaming slots */
+	HostPool *pool; mmg_hit_t *ph; uint64_t ph_bytes; /* streamed: the hit records live in a pinned pool block */
 	/* debug: arenas of the LAST chunk stay valid until the next run */
 	uint32_t dbg_r0, dbg_r1;
 };
@@ -249,6 +297,7 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	CK(cudaEventCreate(&al->ev_run0));
 	CK(cudaEventCreate(&al->ev_run1));
 	al->last_run_ms = 0;
+	al->pool = new HostPool();
 	al->ev_used = 0, al->s_in = 0, al->s_out = 0, al->stream_ready = false, al->d_stats_pool = 0, al->n_sub = 0;
 	memset(al->in_bases, 0, sizeof(al->in_bases)), memset(al->in_off, 0, sizeof(al->in_off)), memset(al->h_in_off, 0, sizeof(al->h_in_off));
 	memset(al->ev_in, 0, sizeof(al->ev_in)), memset(al->ev_free, 0, sizeof(al->ev_free)), memset(al->rs, 0, sizeof(al->rs));
@@ -300,6 +349,17 @@ void mmg_aligner_destroy(mmg_aligner *al)
 		if (r.h_nregs) cudaFreeHost(r.h_nregs);
 	}
 	for (size_t i = 0; i < al->ev_pool.size(); ++i) cudaEventDestroy(al->ev_pool[i]);
+	if (al->pool) {
+		bool del = false;
+		{
+			std::lock_guard<std::mutex> g(al->pool->mu);
+			for (size_t i = 0; i < al->pool->blocks.size(); ++i) cudaFreeHost(al->pool->blocks[i].first);
+			al->pool->blocks.clear();
+			al->pool->dead = true;
+			del = --al->pool->refs == 0;
+		}
+		if (del) delete al->pool;
+	}
 	if (al->ev0) cudaEventDestroy(al->ev0);
 	if (al->ev1) cudaEventDestroy(al->ev1);
 	if (al->ev_run0) cudaEventDestroy(al->ev_run0);
@@ -337,6 +397,7 @@ int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets
 	b->d_bases = 0, b->d_off = 0, b->d_hits = 0, b->d_nregs = 0, b->d_stats = 0, b->d_cigar = 0, b->cigar_cap = 0, b->n_cigar_dev = 0;
 	b->uploaded = b->ran = b->fetched = false;
 	b->streamed = false;
+	b->pool = 0, b->ph = 0, b->ph_bytes = 0;
 	memset(b->stats, 0, sizeof(b->stats));
 	for (uint32_t i = 0; i < n_reads; ++i) {
 		uint64_t l = offsets[i + 1] - offsets[i];
@@ -513,8 +574,6 @@ static int slot_drain(mmg_aligner *al, mmg_batch *b, int k)
 	mmg_aligner::ResSlot &r = al->rs[k];
 	if (!r.pending) return MMG_OK;
 	CK(cudaEventSynchronize(r.ev_out));
-	if (b->hits.size() < r.hit_base + r.n_hits) b->hits.resize(r.hit_base + r.n_hits);
-	if (r.n_hits) memcpy(b->hits.data() + r.hit_base, r.h_hits, r.n_hits * sizeof(mmg_hit_t));
 	if (b->cigar.size() < r.cigar_base + r.n_cigar) b->cigar.resize(r.cigar_base + r.n_cigar);
 	if (r.n_cigar) memcpy(b->cigar.data() + r.cigar_base, r.h_cigar, r.n_cigar * 4);
 	uint64_t acc = r.hit_base;
@@ -616,6 +675,15 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 			int rc;
 			if ((rc = slot_drain(al, b, k))) return rc;
 			if ((rc = slot_grow(&r.d_hits, &r.h_hits, &r.hits_cap, n_hits_sub + 1))) return rc;
+			if ((b->n_hits_dev + n_hits_sub) * sizeof(mmg_hit_t) > b->ph_bytes) { /* rare: more hits than reserved */
+				uint64_t nb = 0;
+				mmg_hit_t *np = (mmg_hit_t*)pool_acquire(b->pool, 2 * (b->n_hits_dev + n_hits_sub) * sizeof(mmg_hit_t), &nb);
+				if (!np) { mmg_set_error("cannot allocate pinned memory for the results"); return MMG_ENOMEM; }
+				CK(cudaStreamSynchronize(al->s_out));
+				memcpy(np, b->ph, b->n_hits_dev * sizeof(mmg_hit_t));
+				pool_release(b->pool, b->ph, b->ph_bytes);
+				b->ph = np, b->ph_bytes = nb;
+			}
 			if ((rc = slot_grow(&r.d_nregs, &r.h_nregs, &r.nregs_cap, (uint64_t)(s1 - s0) + 1))) return rc;
 			if (with_cigar && (rc = slot_grow(&r.d_cigar, &r.h_cigar, &r.cigar_cap, n_cg_sub + 1))) return rc;
 			STAGE_BEGIN();
@@ -625,7 +693,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 			STAGE_END(ST_REGS);
 			CK(cudaEventRecord(r.ev_packed, st));
 			CK(cudaStreamWaitEvent(al->s_out, r.ev_packed, 0));
-			if (n_hits_sub) CK(cudaMemcpyAsync(r.h_hits, r.d_hits, n_hits_sub * sizeof(mmg_hit_t), cudaMemcpyDeviceToHost, al->s_out));
+			if (n_hits_sub) CK(cudaMemcpyAsync(b->ph + b->n_hits_dev, r.d_hits, n_hits_sub * sizeof(mmg_hit_t), cudaMemcpyDeviceToHost, al->s_out));
 			if (n_cg_sub) CK(cudaMemcpyAsync(r.h_cigar, r.d_cigar, n_cg_sub * 4, cudaMemcpyDeviceToHost, al->s_out));
 			CK(cudaMemcpyAsync(r.h_nregs, r.d_nregs, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToHost, al->s_out));
 			CK(cudaEventRecord(r.ev_out, al->s_out));
@@ -659,7 +727,7 @@ static void cut_chunks(const mmg_aligner *al, const mmg_batch *b, std::vector<ui
 		}
 		cuts.push_back(r1);
 		r0 = r1;
-		shift = shift > 2 ? shift - 1 : 0; /* 1/8, 1/4, then full chunks */
+		shift = 0; /* one small first chunk, then full chunks */
 	}
 }
 
@@ -737,7 +805,9 @@ static int map_batch_streamed(mmg_aligner *al, mmg_batch *b)
 	al->rs[0].pending = al->rs[1].pending = false;
 	b->n_hits_dev = 0, b->n_cigar_dev = 0;
 	b->hit_off.assign((size_t)b->n_reads + 1, 0);
-	b->hits.reserve((size_t)b->n_reads + (b->n_reads >> 3) + 16);
+	b->pool = al->pool;
+	b->ph = (mmg_hit_t*)pool_acquire(b->pool, ((uint64_t)b->n_reads + (b->n_reads >> 3) + 1024) * sizeof(mmg_hit_t), &b->ph_bytes);
+	if (!b->ph) { b->pool = 0; mmg_set_error("cannot allocate pinned memory for the results"); return MMG_ENOMEM; }
 	std::vector<uint32_t> cuts;
 	cut_chunks(al, b, cuts, true);
 	const size_t n_chunks = cuts.size() - 1;
@@ -779,7 +849,7 @@ static int map_batch_streamed(mmg_aligner *al, mmg_batch *b)
 	CK(cudaGetLastError());
 	{ float ms = 0; cudaEventElapsedTime(&ms, al->ev_run0, al->ev_run1); al->last_run_ms = ms; }
 	stage_collect(al);
-	b->hits.resize(b->n_hits_dev), b->cigar.resize(b->n_cigar_dev);
+	b->cigar.resize(b->n_cigar_dev);
 	b->hit_off[b->n_reads] = b->n_hits_dev;
 	b->ran = b->fetched = true;
 	return MMG_OK;
@@ -802,6 +872,7 @@ int mmg_map_batch(mmg_aligner *al, const char *bases, const uint64_t *offsets, u
 	b->hits_cap = 0, b->n_hits_dev = 0;
 	b->uploaded = b->ran = b->fetched = false;
 	b->streamed = true;
+	b->pool = 0, b->ph = 0, b->ph_bytes = 0;
 	b->dbg_r0 = b->dbg_r1 = 0;
 	memset(b->stats, 0, sizeof(b->stats));
 	int rc = map_batch_streamed(al, b);
@@ -817,6 +888,7 @@ int mmg_map_batch(mmg_aligner *al, const char *bases, const uint64_t *offsets, u
 void mmg_batch_destroy(mmg_batch *b)
 {
 	if (!b) return;
+	if (b->ph && b->pool) pool_release(b->pool, b->ph, b->ph_bytes);
 	if (b->d_bases) cudaFree(b->d_bases);
 	if (b->d_off) cudaFree(b->d_off);
 	if (b->d_hits) cudaFree(b->d_hits);
@@ -827,9 +899,9 @@ void mmg_batch_destroy(mmg_batch *b)
 }
 
 uint32_t mmg_batch_n_reads(const mmg_batch *b) { return b->n_reads; }
-uint64_t mmg_batch_n_hits(const mmg_batch *b) { return b->hits.size(); }
+uint64_t mmg_batch_n_hits(const mmg_batch *b) { return b->streamed ? b->n_hits_dev : b->hits.size(); }
 const uint64_t *mmg_batch_hit_off(const mmg_batch *b) { return b->hit_off.data(); }
-const mmg_hit_t *mmg_batch_hits(const mmg_batch *b) { return b->hits.data(); }
+const mmg_hit_t *mmg_batch_hits(const mmg_batch *b) { return b->streamed ? b->ph : b->hits.data(); }
 uint64_t mmg_batch_n_cigar(const mmg_batch *b) { return b->cigar.size(); }
 const uint32_t *mmg_batch_cigar(const mmg_batch *b) { return b->cigar.data(); }
 int mmg_batch_stats(const mmg_batch *b, uint64_t out[MMG_N_STATS]) { memcpy(out, b->stats, sizeof(b->stats)); return MMG_OK; }
