@@ -169,6 +169,13 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t value);
  * copy of the results happen inside this call. */
 int mmg_map_batch(mmg_aligner *al, const char *bases, const uint64_t *offsets, uint32_t n_reads, mmg_batch **out);
 
+/* Page-locked host memory for the `bases` buffer of mmg_map_batch: with it the per-chunk host->device copies are
+ * asynchronous and overlap the kernels (a pageable buffer is staged by the driver and blocks the submitting thread).
+ * Replaces nothing in the reference (its FFI passes one `*const c_char` per read, src/lib.rs:482-488); it is what the
+ * batch host (the Rust work-queue drain) should assemble its reads in. */
+int mmg_host_alloc(size_t bytes, void **out);
+void mmg_host_free(void *p);
+
 /* The same path split in three so that device time can be measured with the
  * inputs already resident in HBM: upload (H2D), run (kernels only; returns when
  * the device is done), fetch (D2H + host marshalling). */

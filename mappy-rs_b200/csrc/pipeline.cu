@@ -367,6 +367,15 @@ void mmg_aligner_destroy(mmg_aligner *al)
 	delete al;
 }
 
+int mmg_host_alloc(size_t bytes, void **out)
+{
+	*out = 0;
+	cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+	if (e != cudaSuccess) { mmg_set_error("cudaMallocHost of %llu bytes failed: %s", (unsigned long long)bytes, cudaGetErrorString(e)); return MMG_ENOMEM; }
+	return MMG_OK;
+}
+void mmg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 {
 	if (strcmp(key, "profile") == 0) { al->profile = (int)v; return MMG_OK; }

@@ -54,7 +54,7 @@ HIT_DTYPE = np.dtype([
 STAT_NAMES = ["n_bases", "n_mz", "n_seed", "n_hit", "n_anchor", "n_iter", "n_kept", "n_cell", "n_regs", "n_rechain", "n_dropped"]
 N_STAGES = 12
 
-EXPORTS = ["mmg_set_opt", "mmg_mapopt_update", "mmg_index_open", "mmg_index_build", "mmg_index_build_on", "mmg_debug_int32_peak", "mmg_index_dump", "mmg_index_destroy",
+EXPORTS = ["mmg_host_alloc", "mmg_host_free", "mmg_set_opt", "mmg_mapopt_update", "mmg_index_open", "mmg_index_build", "mmg_index_build_on", "mmg_debug_int32_peak", "mmg_index_dump", "mmg_index_destroy",
            "mmg_index_info", "mmg_index_seq_name", "mmg_index_seq_len", "mmg_index_name2id", "mmg_index_getseq",
            "mmg_index_entries", "mmg_aligner_create", "mmg_aligner_destroy", "mmg_aligner_set", "mmg_map_batch",
            "mmg_batch_upload", "mmg_batch_run", "mmg_batch_fetch", "mmg_batch_n_reads", "mmg_batch_n_hits",
@@ -84,6 +84,8 @@ class Lib:
         L.mmg_index_build.argtypes = [P(IdxOpt), c_int, c_vp, c_vp, c_vp, c_int, P(c_vp)]
         L.mmg_index_build_on.argtypes = [P(IdxOpt), c_int, c_vp, c_vp, c_vp, c_int, c_int, P(c_vp)]
         L.mmg_debug_int32_peak.argtypes = [c_int, P(ctypes.c_double)]
+        L.mmg_host_alloc.argtypes = [ctypes.c_size_t, P(c_vp)]
+        L.mmg_host_free.argtypes = [c_vp]
         L.mmg_index_dump.argtypes = [c_vp, c_cp]
         L.mmg_index_destroy.argtypes = [c_vp]
         L.mmg_index_info.argtypes = [c_vp, c_vp]
@@ -134,6 +136,35 @@ def np_from(ptr, n, dtype, copy=True):
     buf = (ctypes.c_char * nbytes).from_address(ptr)
     a = np.frombuffer(buf, dtype=dtype, count=int(n))
     return a.copy() if copy else a
+
+
+class PinnedBuffer:
+    """Grow-only page-locked byte buffer (mmg_host_alloc) that the batch host assembles its reads in."""
+
+    def __init__(self, lib):
+        self.lib, self.ptr, self.cap, self.arr = lib, None, 0, None
+
+    def view(self, n):
+        if n > self.cap:
+            self.close()
+            cap = max(1 << 20, int(n * 1.5))
+            p = c_vp()
+            self.lib.check(self.lib.L.mmg_host_alloc(cap, ctypes.byref(p)))
+            self.ptr, self.cap = p, cap
+            self.arr = np.frombuffer((ctypes.c_char * cap).from_address(p.value), dtype=np.uint8)
+        return self.arr[:max(n, 1)]
+
+    def close(self):
+        if self.ptr is not None:
+            self.arr = None
+            self.lib.L.mmg_host_free(self.ptr)
+            self.ptr, self.cap = None, 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Index:

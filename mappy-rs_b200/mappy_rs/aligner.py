@@ -172,6 +172,7 @@ class Aligner:
         for key, val in (_tune or {}).items():   # device arena sizes (not mapping semantics)
             self._aligner.set(key, val)
         self._lock = threading.Lock()
+        self._pinned = _mmg.PinnedBuffer(lib)
 
     # ---- index accessors ------------------------------------------------------------
     def __bool__(self):
@@ -213,11 +214,14 @@ class Aligner:
         bs = [s.encode() for s in seqs]
         offs = np.zeros(len(bs) + 1, dtype=np.uint64)
         offs[1:] = np.cumsum([len(b) for b in bs])
-        buf = np.frombuffer(b"".join(bs), dtype=np.uint8) if offs[-1] else np.zeros(1, dtype=np.uint8)
         with self._lock:
+            # the reads are assembled in page-locked memory: the library's chunked host->device copies then overlap its kernels
+            buf = self._pinned.view(int(offs[-1]))
+            if offs[-1]:
+                buf[:] = np.frombuffer(b"".join(bs), dtype=np.uint8)
             res = self._aligner.map_batch(buf, offs)
-        cs_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 0) if cs else None
-        md_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 1) if md else None
+            cs_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 0) if cs else None   # reads the shared pinned buffer
+            md_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 1) if md else None
         ho = res.hit_off
         return [_mappings_from(res, self._names, self._lens, cs_l, md_l, int(ho[i]), int(ho[i + 1])) for i in range(len(bs))]
 
@@ -313,6 +317,9 @@ class Aligner:
         for t in getattr(self, "_workers", []):   # device buffers must outlive in-flight batches
             t.join()
         self._workers = []
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned.close()
+            self._pinned = None
         if self._aligner is not None:
             self._aligner.close()
             self._aligner = None
