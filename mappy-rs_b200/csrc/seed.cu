@@ -358,12 +358,7 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 #define AF_MAX_SEEDS 3072
 #define AF_MAX_ANCHORS 65536
 #define AF_MIN_ANCHORS 64
-#define AF_BIG 256              /* listed high-occurrence seeds per read */
-#ifdef MMG_EMU
-#define AF_WARP_SEED 4          /* the CPU test-suite sends seeds with > 4 hits down the per-warp path so that it is exercised */
-#else
-#define AF_WARP_SEED 32         /* seeds with more hits are gathered by a whole warp */
-#endif
+#define AF_GATHER 4             /* independent pos[] reads in flight per thread */
 
 /* hashed slot of the position bin (strand, contig, (pos >> shift) + delta) in a table of 2^bits bins */
 __device__ __forceinline__ uint32_t af_bin_slot(uint64_t rr, bool rev, int shift, int delta, uint32_t seed, int bits)
@@ -385,7 +380,7 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 {
 	MMG_DYN_SMEM(smem_raw);
 	uint32_t *s_tab = (uint32_t*)smem_raw, *s_two = s_tab + AF_TAB, *s_pre = s_two + AF_TAB, *s_bits = s_pre + AF_MAX_SEEDS + 1;
-	__shared__ uint32_t s_item, s_dup, s_keep, s_nbig, s_warp[AF_THREADS / 32], s_big[AF_BIG];
+	__shared__ uint32_t s_item, s_dup, s_keep, s_warp[AF_THREADS / 32];
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 	unsigned long long dropped = 0;
 	for (;;) {
@@ -459,37 +454,32 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 			const uint32_t seed = round ? 0x68E31DA4u : 0u;
 			for (int j = tid; j < (1 << (bits - 5)); j += AF_THREADS) s_tab[j] = 0, s_two[j] = 0;
 			__syncthreads();
-			if (round == 0) { /* seeds with few hits one per thread; seeds with many hits are listed and taken one per warp */
-				if (tid == 0) s_nbig = 0;
-				__syncthreads();
-				for (int i = tid; i < n_m; i += AF_THREADS) {
-					const uint32_t cnt = sn[i];
-					if (cnt > AF_WARP_SEED) { const uint32_t q = atomicAdd(&s_nbig, 1u); if (q < AF_BIG) s_big[q] = (uint32_t)i; continue; }
-					const uint64_t val = sv[i], qbit = (uint64_t)(sq[i] & 1u) << 63;
-					const uint32_t g0 = s_pre[i];
-					for (uint32_t k = 0; k < cnt; ++k) {
-						const uint64_t rr = cnt == 1 ? val : di.pos[val + k];
-						hits[g0 + k] = rr | qbit;
-						const uint32_t b0 = af_bin_slot(rr, (rr & 1) != (qbit >> 63), shift, 0, seed, bits);
-						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+			if (round == 0) {
+				/* one thread per HIT (the seed that owns hit g is found by binary search in the prefix sums), AF_GATHER
+				 * independent random reads of pos[] in flight per thread before any of them is used */
+				for (uint32_t gb = tid; gb < n_full; gb += AF_THREADS * AF_GATHER) {
+					uint64_t rr[AF_GATHER], qb[AF_GATHER];
+#pragma unroll
+					for (int u = 0; u < AF_GATHER; ++u) {
+						const uint32_t g = gb + (uint32_t)u * AF_THREADS;
+						rr[u] = 0, qb[u] = 0;
+						if (g < n_full) {
+							int lo = 0, hi = n_m - 1; /* largest i with s_pre[i] <= g */
+							while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[mid] <= g) lo = mid; else hi = mid - 1; }
+							const uint32_t cnt = sn[lo];
+							const uint64_t val = sv[lo];
+							qb[u] = (uint64_t)(sq[lo] & 1u) << 63;
+							rr[u] = cnt == 1 ? val : di.pos[val + (g - s_pre[lo])];
+						}
 					}
-				}
-				__syncthreads();
-				const uint32_t n_big = s_nbig;
-#ifdef MMG_EMU
-				if (tid == 0 && n_big && getenv("MMG_AF_DEBUG")) fprintf(stderr, "[af] read %u: %u seeds with more than AF_WARP_SEED hits\n", r, n_big);
-#endif
-				const bool listed = n_big <= AF_BIG; /* otherwise every warp scans the seeds for its share */
-				for (uint32_t q = wib; q < (listed ? n_big : (uint32_t)n_m); q += AF_THREADS / 32) {
-					const uint32_t i = listed ? s_big[q] : q, cnt = sn[i];
-					if (cnt <= AF_WARP_SEED) continue;
-					const uint64_t val = sv[i], qbit = (uint64_t)(sq[i] & 1u) << 63;
-					const uint32_t g0 = s_pre[i];
-					for (uint32_t k = lane; k < cnt; k += 32) {
-						const uint64_t rr = di.pos[val + k];
-						hits[g0 + k] = rr | qbit;
-						const uint32_t b0 = af_bin_slot(rr, (rr & 1) != (qbit >> 63), shift, 0, seed, bits);
-						if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+#pragma unroll
+					for (int u = 0; u < AF_GATHER; ++u) {
+						const uint32_t g = gb + (uint32_t)u * AF_THREADS;
+						if (g < n_full) {
+							hits[g] = rr[u] | qb[u];
+							const uint32_t b0 = af_bin_slot(rr[u], (rr[u] & 1) != (qb[u] >> 63), shift, 0, seed, bits);
+							if (atomicOr(&s_tab[b0 >> 5], 1u << (b0 & 31)) >> (b0 & 31) & 1u) atomicOr(&s_two[b0 >> 5], 1u << (b0 & 31));
+						}
 					}
 				}
 			} else {
