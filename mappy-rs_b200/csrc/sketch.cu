@@ -26,6 +26,8 @@
 #include "dev_common.cuh"
 #include "stages.h"
 
+#define SK_LEVELS 4   /* level rings of the doubling window minimum: w <= 32 */
+
 template<typename KT> struct SkKey;
 /* k <= 15: a k-mer and its hash fit 30 bits, every step is 32-bit arithmetic (hash64 restricted to 2k <= 30
  * bits only ever reads the low 2k bits of its intermediates, so the 32-bit evaluation is bit-identical) */
@@ -106,6 +108,10 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 	KT *xr = (KT*)smem_raw + (size_t)wib * RING;
 	uint32_t *yr = (uint32_t*)((KT*)smem_raw + (size_t)SKETCH_WARPS * RING) + (size_t)wib * RING;
 	uint32_t *lr = (uint32_t*)((KT*)smem_raw + (size_t)SKETCH_WARPS * RING) + (size_t)SKETCH_WARPS * RING + (size_t)wib * RING;
+	/* level rings of the doubling window minimum (RING == 64, w <= 32: levels 1..4), after the three base rings */
+	unsigned char *lvl_base = smem_raw + (size_t)SKETCH_WARPS * RING * (sizeof(KT) + 8) + (size_t)wib * SK_LEVELS * RING * (sizeof(KT) + 4);
+	KT *lvl_v = (KT*)lvl_base;
+	uint32_t *lvl_m = (uint32_t*)(lvl_base + (size_t)SK_LEVELS * RING * sizeof(KT));
 	const KT mask = (KT)(((uint64_t)1 << 2 * k) - 1), INF = K::inf();
 	const uint32_t lt = mmg_lanemask_lt();
 	unsigned long long tot_mz = 0, tot_bases = 0;
@@ -123,6 +129,7 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 		uint32_t *oy = c.mz_y + base;
 
 		for (int j = lane; j < RING; j += 32) xr[j] = INF;
+		if (RING == 64) for (int j = lane; j < SK_LEVELS * RING; j += 32) lvl_v[j] = INF, lvl_m[j] = 1u << 8;
 		__syncwarp();
 
 		uint64_t prev = 0;          /* last 32 usable bases, newest in the low bits */
@@ -186,8 +193,43 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 			const int e = e_base + lane;
 			KT xe = INF, bxv = INF;
 			int le = 0, bj = e, neq = 0;
-			if (act) {
-				xe = xr[e & RM], le = (int)lr[e & RM];
+			if (act) xe = xr[e & RM], le = (int)lr[e & RM];
+			if (RING == 64) {
+				/* P(e) by doubling: A_k[e] summarises the 2^k events ending at e as (minimum, age of its newest copy, number
+				 * of copies); A_k[e] = A_(k-1)[e] (+) A_(k-1)[e - 2^(k-1)].  The window of w events is the disjoint union of
+				 * one piece per set bit of w, newest first: A_K[e] from registers, the others from the level rings (events of
+				 * earlier steps left theirs there).  log2(w) combines instead of w. */
+				KT cv = xe;
+				uint32_t cm = 1u << 8; /* age 0, one copy */
+				int K = 0;
+				while ((2 << K) <= w) ++K;
+				for (int q = 1; q <= K; ++q) {
+					const int half = 1 << (q - 1);
+					KT *lv = lvl_v + (size_t)(q > 1 ? q - 2 : 0) * RING;   /* ring of level q-1 (levels >= 1 sit at index level-1) */
+					uint32_t *lm = lvl_m + (size_t)(q > 1 ? q - 2 : 0) * RING;
+					if (q > 1 && act) lv[e & RM] = cv, lm[e & RM] = cm; /* level q-1 of this event (level 0 is xr itself) */
+					__syncwarp();
+					if (act) {
+						const KT ov = q == 1 ? xr[(e - half) & RM] : lv[(e - half) & RM];
+						const uint32_t om = q == 1 ? (1u << 8) : lm[(e - half) & RM];
+						if (ov < cv) cv = ov, cm = om + (uint32_t)half;       /* older piece wins: its ages shift by the newer piece's size */
+						else if (ov == cv) cm += om & 0xffffff00u;          /* tie: newest copy stays, counts add */
+					}
+				}
+				/* the pieces of the lower set bits of w lie behind the 2^K newest events */
+				int off = 1 << K;
+				for (int q = K - 1; q >= 0; --q) {
+					if (!((w >> q) & 1)) continue;
+					if (act) {
+						const KT ov = q == 0 ? xr[(e - off) & RM] : (lvl_v + (size_t)(q - 1) * RING)[(e - off) & RM];
+						const uint32_t om = q == 0 ? (1u << 8) : (lvl_m + (size_t)(q - 1) * RING)[(e - off) & RM];
+						if (ov < cv) cv = ov, cm = om + (uint32_t)off;
+						else if (ov == cv) cm += om & 0xffffff00u;
+					}
+					off += 1 << q;
+				}
+				if (act) bxv = cv, bj = e - (int)(cm & 0xffu), neq = (int)(cm >> 8);
+			} else if (act) {
 				for (int j = e - w + 1; j <= e; ++j) {      /* P(e): newest among equal keys; neq = copies of it in the window */
 					const KT vx = xr[j & RM];
 					const bool less = vx < bxv, same = vx == bxv;
@@ -241,7 +283,7 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 template<int RING, typename KT>
 static void launch_sketch_t(const ChunkDev &c, int w, int k, int grid, cudaStream_t st, uint32_t *work)
 {
-	size_t smem = (size_t)SKETCH_WARPS * RING * (sizeof(KT) + 8);
+	size_t smem = (size_t)SKETCH_WARPS * RING * (sizeof(KT) + 8) + (RING == 64 ? (size_t)SKETCH_WARPS * SK_LEVELS * RING * (sizeof(KT) + 4) : 0);
 	if (smem > 48 * 1024) {
 		static bool attr_done = false;
 		if (!attr_done) { cudaFuncSetAttribute(sketch_kernel<RING, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }

@@ -286,3 +286,37 @@ def test_isolated_anchor_filter_is_exact(emu_lib, oracle_mod):
         assert dev2.stats["n_dropped"] == 0 and parity.compare_hits(dev2, ora) == []
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("k,w", [(15, 1), (15, 2), (15, 3), (15, 7), (13, 16), (15, 31), (15, 32), (17, 19), (21, 11), (15, 40)])
+def test_sketch_window_sizes(emu_lib, oracle_mod, k, w):
+    """The doubling window minimum of the sketch kernel (w <= 32) decomposes w by its bits; w > 32 takes the scan.
+    Minimizers (order included) must equal mm_sketch for every shape of w, with N runs, homopolymers and short reads."""
+    import ctypes
+    from mappy_rs import _mmg
+    ref, coff, names, seqs = parity.random_reference(200 + w, [40000])
+    io, mo = _mmg.IdxOpt(), _mmg.MapOpt()
+    emu_lib.check(emu_lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mo)))
+    io.k, io.w = k, w
+    mo.flag = 0
+    idx = _mmg.Index.build(emu_lib, io, names, seqs)
+    emu_lib.check(emu_lib.L.mmg_mapopt_update(ctypes.byref(mo), idx.h))
+    al = _mmg.DeviceAligner(emu_lib, idx, mo)
+    ora = oracle_mod.Oracle(names=names, seqs=seqs, k=k, w=w)
+    ora.set_opt("flag", 0)
+    try:
+        base = ref[3000:9000].tobytes().decode()
+        reads = [base, base[:k - 1], base[:k], base[:k + w - 1], base[:k + w], base[:k + w + 1], base[:700] + "N" * 3 + base[700:1500] + "N" + base[1500:1600],
+                 "A" * 300 + base[:400] + "ACAC" * 50, base[:2000].lower(), "".join(c if i % 37 else "N" for i, c in enumerate(base[:3000])), base[::-1][:1234]]
+        buf, offs = oracle_mod.pack_reads(reads)
+        res = al.map_batch(buf, offs, keep_handle=True)
+        mx, my, moff = al.debug_dump(res.handle, 0, int(offs[-1]) + 16, len(reads))
+        al.free(res.handle)
+        for i, s in enumerate(reads):
+            mv = ora.trace(s.encode())["mv"]      # mm_sketch followed by mm_seed_mz_flt, as the device dump
+            sl = slice(int(moff[i]), int(moff[i + 1]))
+            assert np.array_equal(mx[sl], mv["x"]) and np.array_equal(my[sl], mv["y"]), (k, w, i)
+    finally:
+        al.close()
+        idx.close()
+        ora.close()
