@@ -58,6 +58,13 @@ __device__ __forceinline__ int32_t dev_comput_sc(uint64_t aix, uint64_t aiy, uin
 	return sc;
 }
 
+/* is anchor a (a <= b in sort order) outside b's window: another strand/contig, or more than d behind on the target?
+ * Same strand and contig means equal high words, and then the low words (target positions) are ordered like the keys. */
+__device__ __forceinline__ bool chain_out_of_range(uint64_t a, uint64_t b, uint32_t d)
+{
+	return (uint32_t)(a >> 32) != (uint32_t)(b >> 32) || (uint32_t)b - (uint32_t)a > d;
+}
+
 __global__ void __launch_bounds__(CHAIN_WARPS * 32)
 chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 {
@@ -95,7 +102,7 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 				const int j = i + lane;
 				uint64_t xj = 0, xp = 0;
 				if (j < n) { xj = ax[j]; if (j > 0) xp = ax[j - 1]; }
-				const bool iso = j < n && (j == 0 || (xp >> 32) != (xj >> 32) || xj > xp + (uint64_t)max_dist_x);
+				const bool iso = j < n && (j == 0 || chain_out_of_range(xp, xj, (uint32_t)max_dist_x));
 				const uint32_t im = __ballot_sync(MMG_FULL, iso);
 				const int run = im == MMG_FULL ? 32 : __ffs((int)~im) - 1;
 				if (run > 0) {
@@ -113,10 +120,10 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 			const uint64_t aix = ax[i], aiy = ay[i];
 			/* advance st: first j that shares the target strand and is within max_dist_x (usually st itself still is) */
 			bool st_out;
-			{ const uint64_t xs = ax[st]; st_out = st < i && ((xs >> 32) != (aix >> 32) || aix > xs + (uint64_t)max_dist_x); }
+			st_out = st < i && chain_out_of_range(ax[st], aix, (uint32_t)max_dist_x);
 			while (st_out) {
 				int j = st + lane;
-				bool out = j < i && ((ax[j] >> 32) != (aix >> 32) || aix > ax[j] + (uint64_t)max_dist_x);
+				bool out = j < i && chain_out_of_range(ax[j], aix, (uint32_t)max_dist_x);
 				uint32_t m = __ballot_sync(MMG_FULL, out);
 				int lead = m == MMG_FULL ? 32 : __ffs((int)~m) - 1;
 				st += lead;
