@@ -358,7 +358,7 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 #define AF_MAX_SEEDS 3072
 #define AF_MAX_ANCHORS 65536
 #define AF_MIN_ANCHORS 64
-#define AF_GATHER 4             /* independent pos[] reads in flight per thread */
+#define AF_GATHER 8             /* independent pos[] reads in flight per thread */
 
 /* hashed slot of the position bin (strand, contig, (pos >> shift) + delta) in a table of 2^bits bins */
 __device__ __forceinline__ uint32_t af_bin_slot(uint64_t rr, bool rev, int shift, int delta, uint32_t seed, int bits)
