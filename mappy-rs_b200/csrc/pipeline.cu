@@ -79,6 +79,10 @@ struct mmg_aligner {
 	std::vector<void*> dev_allocs;     /* index + arenas */
 	/* arena capacities */
 	uint64_t cap_bases, cap_anchors, cap_regs, cap_keep_words;
+	int dual_min;                      /* fewest reads of a chunk for which the two-stream split is used */
+	int dual_stream;                   /* 1 = the two halves of a chunk run expand..re-chain on two streams (tuning knob "dual_stream") */
+	cudaStream_t st2;
+	cudaEvent_t ev_fork, ev_join;
 	int ramp_shift;                    /* streamed mode: the first chunk is 1/2^ramp_shift of the arena (tuning knob "ramp_shift") */
 	int anchor_filter;                 /* 1 = drop isolated anchors before the sort (seed.cu anchor_filter_kernel) */
 	uint32_t cap_reads;
@@ -259,7 +263,8 @@ read_order_kernel(const uint64_t *off, uint32_t n, uint32_t *order)
 	__syncthreads();
 	for (uint32_t i = tid; i < n; i += 1024) {
 		const uint64_t l = (off[i + 1] - off[i]) >> 6;
-		order[atomicAdd(&s_bin[4095 - (l > 4095 ? 4095u : (uint32_t)l)], 1u)] = i;
+		const uint32_t p = atomicAdd(&s_bin[4095 - (l > 4095 ? 4095u : (uint32_t)l)], 1u); /* rank, longest first */
+		order[(p & 1u) ? (n + 1) / 2 + p / 2 : p / 2] = i;   /* even ranks, then odd ranks: two balanced halves, each longest first */
 	}
 }
 
@@ -313,6 +318,10 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 		al->cap_keep_words = (uint64_t)1 << 24;
 	}
 	al->anchor_filter = 1;
+	al->dual_stream = 1, al->dual_min = 4096;
+	CK(cudaStreamCreateWithFlags(&al->st2, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&al->ev_fork, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&al->ev_join, cudaEventDisableTiming));
 	al->ramp_shift = 1;
 	al->cap_tb = (uint64_t)32 << 30, al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48, al->big_per_warp = (uint64_t)1 << 20;
 	memset(&al->xb, 0, sizeof(al->xb));
@@ -332,6 +341,9 @@ void mmg_aligner_destroy(mmg_aligner *al)
 	if (!al) return;
 	for (size_t i = 0; i < al->dev_allocs.size(); ++i) cudaFree(al->dev_allocs[i]);
 	if (al->stream) cudaStreamDestroy(al->stream);
+	if (al->st2) cudaStreamDestroy(al->st2);
+	if (al->ev_fork) cudaEventDestroy(al->ev_fork);
+	if (al->ev_join) cudaEventDestroy(al->ev_join);
 	if (al->s_in) cudaStreamDestroy(al->s_in);
 	if (al->s_out) cudaStreamDestroy(al->s_out);
 	for (int k = 0; k < 2; ++k) {
@@ -381,6 +393,8 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 	if (strcmp(key, "profile") == 0) { al->profile = (int)v; return MMG_OK; }
 	if (strcmp(key, "sort_small_max") == 0) { mmg_sort_set_small_max((int)v); return MMG_OK; }
 	if (strcmp(key, "anchor_filter") == 0) { al->anchor_filter = v != 0; return MMG_OK; }
+	if (strcmp(key, "dual_stream") == 0) { al->dual_stream = v != 0; return MMG_OK; }
+	if (strcmp(key, "dual_min") == 0) { al->dual_min = v < 2 ? 2 : (int)v; return MMG_OK; }
 	if (strcmp(key, "ramp_shift") == 0) { al->ramp_shift = v < 0 ? 0 : v > 6 ? 6 : (int)v; return MMG_OK; }
 	if (al->arenas_ready) { mmg_set_error("arena sizes are fixed after the first batch"); return MMG_EINVAL; }
 	if (strcmp(key, "chunk_bases") == 0) al->cap_bases = (uint64_t)v;
@@ -640,12 +654,39 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 			if (s1 == s0) { mmg_set_error("read %u has %llu anchors, more than anchor_cap", r0 + s0, (unsigned long long)(h_aoff[s0 + 1] - h_aoff[s0])); return MMG_ENOMEM; }
 			c.a_off0 = h_aoff[s0];
 		}
-		if (wi + 12 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
+		if (wi + 24 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
+		if (al->dual_stream && !al->profile && !split && c.order && s1 - s0 >= (uint32_t)al->dual_min) {
+			/* Every kernel of expand -> sort -> chain -> backtrack -> re-chain ends with a tail in which a few long reads
+			 * (or equal-key replays) keep a handful of SMs busy.  The reads are cut in two interleaved halves (the work
+			 * order puts the even ranks first, the odd ranks second) that go through these stages on two streams: the
+			 * tail of one half's kernel is filled by the other half's next kernel.  Same arenas (the halves own disjoint
+			 * slices), separate work counters and deferred-read lists.  Per-stage events would overlap, so stage timing
+			 * ("profile") keeps the single-stream order. */
+			const uint32_t mid = s0 + (s1 - s0 + 1) / 2;
+			ChunkDev c2 = c;
+			c2.big_list = c.big_list + al->cap_reads / 2, c2.tie_list = c.tie_list + al->cap_reads / 2;
+			CK(cudaEventRecord(al->ev_fork, st));
+			CK(cudaStreamWaitEvent(al->st2, al->ev_fork, 0));
+			for (int h = 0; h < 2; ++h) {
+				const ChunkDev &ch = h ? c2 : c;
+				cudaStream_t sh = h ? al->st2 : st;
+				const uint32_t a = h ? mid : s0, bnd = h ? s1 : mid;
+				launch_expand(ch, al->di, al->dopt, a, bnd, al->n_sms, sh, work + wi++);
+				launch_sort(ch, al->di, a, bnd, al->n_sms, sh, work + wi); wi += 5;
+				launch_chain(ch, al->dopt, a, bnd, al->n_sms, sh, work + wi++);
+				launch_backtrack(ch, al->dopt, a, bnd, al->n_sms, sh, work + wi++);
+				launch_rechain(ch, al->dopt, a, bnd, al->rmq_nodes, al->n_sms, sh, work + wi++);
+			}
+			CK(cudaEventRecord(al->ev_join, al->st2));
+			CK(cudaStreamWaitEvent(st, al->ev_join, 0));
+			al->stage_launches[ST_EXPAND] += 2, al->stage_launches[ST_SORT] += 2, al->stage_launches[ST_CHAIN] += 2, al->stage_launches[ST_BACKTRACK] += 2, al->stage_launches[ST_RECHAIN] += 2;
+		} else {
 		STAGE_BEGIN(); launch_expand(c, al->di, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_EXPAND);
 		STAGE_BEGIN(); launch_sort(c, al->di, s0, s1, al->n_sms, st, work + wi); wi += 5; STAGE_END(ST_SORT);
 		STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
 		STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
 		STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);
+		}
 		const bool with_cigar = (al->mo.flag & MMG_F_CIGAR) != 0;
 		STAGE_BEGIN();
 		if (with_cigar) { /* region slices leave room for the pieces z-drop splits insert */

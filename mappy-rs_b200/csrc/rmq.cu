@@ -412,7 +412,7 @@ rechain_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, uin
 		if (lane == 0) {
 			dev_radix_sort_128x(ax, ay, n, s_bkt[wib], (int*)v);
 			dev_lchain_rmq(o.max_gap, o.rmq_inner_dist, o.bw_long, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
-			               n, ax, ay, f, p, t, nodes + 2 * ab + 2 * (uint64_t)(r - r0));
+			               n, ax, ay, f, p, t, nodes + 2 * ab + 2 * (uint64_t)r); /* disjoint per read: 2 nodes per anchor + 2 (the arena holds 2 * (anchors + reads) nodes) */
 			c.flags[r] |= 2u;
 		}
 		__syncwarp();

@@ -172,6 +172,25 @@ def test_cigar_mode_fixture_map_one(emu_lib, oracle_mod):
         c.close()
 
 
+def test_two_stream_halves_equal_oracle(emu_lib, oracle_mod):
+    """dual_min = 2 sends even a small chunk through the two-stream split of expand..re-chain (interleaved halves,
+    separate work counters and deferred-read lists); repeats, chimeras and equal-key reads included."""
+    ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
+    c = parity.Case(emu_lib, names, seqs)
+    try:
+        c.aligner.set("dual_min", 2)
+        c.aligner.set("sort_small_max", 300)
+        b1, o1 = data_gen.make_sv_reads(52, ref, coff, 120)
+        b2, o2 = oracle_mod.pack_reads(_dup_reads(ref[:300000], 9, 53))
+        buf = np.concatenate([b1, b2]); offs = np.concatenate([o1, o2[1:] + o1[-1]])
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
+    finally:
+        c.aligner.set("sort_small_max", 512)
+        c.close()
+
+
 def test_long_reads_use_large_tiles(emu_lib, oracle_mod):
     """Reads whose anchors exceed the small shared-memory tiles (sort: 2048 records) take the
     deferred large-tile passes; results must not change."""
