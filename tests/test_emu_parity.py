@@ -178,6 +178,7 @@ def test_two_stream_halves_equal_oracle(emu_lib, oracle_mod):
     ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
     c = parity.Case(emu_lib, names, seqs)
     try:
+        c.aligner.set("dual_stream", 1)
         c.aligner.set("dual_min", 2)
         c.aligner.set("sort_small_max", 300)
         b1, o1 = data_gen.make_sv_reads(52, ref, coff, 120)
