@@ -14,6 +14,7 @@
  * polynomial evaluated in double) that the CPU test-suite checks against the
  * host libm over every positive normal float.
  */
+#include <string.h>
 #include "dev_common.cuh"
 #include "dev_sort.cuh"
 #include "dev_regs.cuh"
@@ -83,6 +84,7 @@ pack_hits_kernel(ChunkDev c, uint32_t r0, uint32_t r1, mmg_hit_t *hits)
 		for (int i = mmg_lane(); i < n; i += 32) {
 			const DevReg g = regs[i];
 			mmg_hit_t o;
+			memset(&o, 0, sizeof(o)); /* padding bytes included: a batch mapped twice returns identical bytes */
 			o.rid = g.rid, o.rs = g.rs, o.re = g.re, o.qs = g.qs, o.qe = g.qe;
 			o.mlen = g.mlen, o.blen = g.blen;
 			o.score = g.score, o.score0 = g.score0, o.cnt = g.cnt, o.subsc = g.subsc, o.n_sub = g.n_sub;
