@@ -224,6 +224,11 @@ def _primary(dev, n):
     return np.where(has, first, -1)
 
 
+def _same_hits(x, y):
+    """field by field (numpy does not copy the padding bytes of an aligned record)"""
+    return x.shape == y.shape and all(np.array_equal(x[f], y[f]) for f in x.dtype.names)
+
+
 def test_full_size_properties_human_scale(gpu_lib):
     """BASELINE.json configs[2] at full reference size (3.1 Gb, 24 contigs; index built on the device): properties
     that need no oracle - simulated reads come back at their origin, results do not depend on how the batch is cut
@@ -249,11 +254,11 @@ def test_full_size_properties_human_scale(gpu_lib):
         assert ok.mean() > 0.99, ok.mean()     # the rest: reads drawn across a contig boundary, chain ends trimmed by errors
         assert (h["mapq"][ok] == 60).mean() > 0.98
         b = al.map_batch(buf, offs)                                          # idempotence
-        assert np.array_equal(a.hit_off, b.hit_off) and a.hits.tobytes() == b.hits.tobytes()
+        assert np.array_equal(a.hit_off, b.hit_off) and _same_hits(a.hits, b.hits)
         half = n // 2                                                        # two calls of half the reads each
         c1 = al.map_batch(buf[:int(offs[half])], offs[:half + 1])
         c2 = al.map_batch(buf[int(offs[half]):], offs[half:] - offs[half])
-        assert a.hits.tobytes() == c1.hits.tobytes() + c2.hits.tobytes()
+        assert _same_hits(a.hits, np.concatenate([c1.hits, c2.hits]))
     finally:
         al.close()
         idx.close()
