@@ -234,7 +234,6 @@ static __device__ uint64_t *rsort_read(const uint64_t *srcx, int n, const uint64
  * (key, source index) staged in shared memory (the cycle-leader permutation is a chain of dependent accesses: the
  * latency of shared memory instead of L2), the stable leaf insertion sorts are replaced by a second radix sort on
  * (key, position after those passes) - see the tie path of sort_kernel. */
-#define RSORT_SMEM_N 2048          /* reads up to this many anchors sort in shared memory (32 KB of records per CTA) */
 #define RSORT_TIE_TILE 12288      /* records staged in shared memory by the equal-key replay (144 KB + 27 KB of per-warp buckets: one CTA per SM; these reads are rare) */
 template<bool TIE>
 __global__ void __launch_bounds__(RSORT_WARPS * 32)
@@ -274,11 +273,9 @@ radix_sort_kernel(ChunkDev c, const uint64_t *seq_off, uint32_t *work, const uin
 			srcx = zy, srcy = zy + n;
 		}
 		if (n > 1) {
-			/* the records ping-pong in shared memory when the read fits (no L2 round trip between the phases of a
-			 * pass), else in the read's global scratch */
-			uint64_t *pa = zx, *pb = zx + n;
-			if (!TIE && n <= RSORT_SMEM_N) pa = (uint64_t*)smem_raw, pb = pa + RSORT_SMEM_N;
-			const uint64_t *S = rsort_read(srcx, n, seq_off, pa, pb, s_cnt, s_red);
+			/* the records ping-pong in the read's global scratch (L2 resident); staging them in shared memory was measured
+			 * slower: it costs 3 of the 8 resident CTAs per SM */
+			const uint64_t *S = rsort_read(srcx, n, seq_off, zx, zx + n, s_cnt, s_red);
 			int tie = 0;
 			for (int i = tid; i < n; i += nt) {
 				const uint64_t rec = S[i];
@@ -307,7 +304,7 @@ int launch_sort(const ChunkDev &c, const DevIndex &di, uint32_t r0, uint32_t r1,
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
 	MMG_LAUNCH((sort_kernel<SORT_SMALL_ELEMS, false>), grid, SORT_THREADS, smem_small, st, c, r0, r1, work, c.big_list, work + 1, g_sort_small_max);
-	MMG_LAUNCH((radix_sort_kernel<false>), grid, RSORT_WARPS * 32, (size_t)RSORT_SMEM_N * 16, st, c, di.seq_off, work + 2, (const uint32_t*)c.big_list, (const uint32_t*)(work + 1), c.tie_list, work + 3);
+	MMG_LAUNCH((radix_sort_kernel<false>), grid, RSORT_WARPS * 32, 0, st, c, di.seq_off, work + 2, (const uint32_t*)c.big_list, (const uint32_t*)(work + 1), c.tie_list, work + 3);
 	const size_t smem_tie = (size_t)RSORT_TIE_TILE * 12;
 	static bool attr_done = false;
 	if (!attr_done) { cudaFuncSetAttribute(radix_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tie); attr_done = true; }
