@@ -150,7 +150,7 @@ template<typename T> static int dev_alloc(mmg_aligner *al, T **p, uint64_t n)
 	if (e != cudaSuccess) { mmg_set_error("cudaMalloc of %llu bytes failed: %s", (unsigned long long)(n * sizeof(T)), cudaGetErrorString(e)); return MMG_ENOMEM; }
 	al->dev_allocs.push_back(q);
 	*p = (T*)q;
-	if (getenv("MMG_POISON")) cudaMemset(q, 0xCD, n * sizeof(T)); /* test hook: nothing may depend on what cudaMalloc returns */
+	if (getenv("MMG_POISON")) cudaMemset(q, 0xCD, n * sizeof(T)), cudaDeviceSynchronize(); /* test hook: nothing may depend on what cudaMalloc returns */
 	return MMG_OK;
 }
 
@@ -588,7 +588,7 @@ template<typename T> static int slot_grow(T **d, T **h, uint64_t *cap, uint64_t 
 		mmg_set_error("cannot allocate %llu bytes for a result slot", (unsigned long long)(n * sizeof(T)));
 		return MMG_ENOMEM;
 	}
-	if (getenv("MMG_POISON")) cudaMemset(*d, 0xCD, n * sizeof(T));
+	if (getenv("MMG_POISON")) cudaMemset(*d, 0xCD, n * sizeof(T)), cudaDeviceSynchronize();
 	*cap = n;
 	return MMG_OK;
 }

@@ -285,3 +285,30 @@ def test_reverse_complement_symmetry(case5mb):
     ha, hb = a.hits[pa[both]], b.hits[pb[both]]
     same = (ha["rid"] == hb["rid"]) & (ha["rs"] == hb["rs"]) & (ha["re"] == hb["re"]) & (ha["rev"] != hb["rev"]) & (ha["score"] == hb["score"])
     assert same.mean() > 0.99, same.mean()
+
+
+def test_no_dependence_on_what_cudamalloc_returns(gpu_lib, oracle_mod):
+    """MMG_POISON fills every device arena with 0xCD right after allocation: mapping-only (filter, radix sort, re-chain)
+    and CIGAR mode (splits, inversions) must still equal the oracle, i.e. nothing reads memory it has not written."""
+    os.environ["MMG_POISON"] = "1"
+    try:
+        ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
+        for cigar in (False, True):
+            c = parity.Case(gpu_lib, names, seqs, cigar=cigar)
+            try:
+                buf, offs = data_gen.make_sv_reads(57, ref, coff, 400)
+                dev = c.aligner.map_batch(buf, offs)
+                ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+                assert parity.compare_hits(dev, ora) == []
+            finally:
+                c.close()
+        c, ref, coff = _random_hit_case(gpu_lib, oracle_mod, 30_000_000, 103, 13, 5, 0)
+        try:
+            buf, offs, _ = data_gen.make_reads(104, ref, coff, 1500, 1000, 8000)
+            dev = c.aligner.map_batch(buf, offs)
+            ora = c.oracle.map_batch(buf, offs, os.cpu_count() or 8)
+            assert dev.stats["n_dropped"] > 0 and parity.compare_stats(dev, ora) == [] and parity.compare_hits(dev, ora) == []
+        finally:
+            c.close()
+    finally:
+        del os.environ["MMG_POISON"]
