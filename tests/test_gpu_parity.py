@@ -302,7 +302,7 @@ def test_no_dependence_on_what_cudamalloc_returns(gpu_lib, oracle_mod):
                 assert parity.compare_hits(dev, ora) == []
             finally:
                 c.close()
-        c, ref, coff = _random_hit_case(gpu_lib, oracle_mod, 30_000_000, 103, 13, 5, 0)
+        c, ref, coff = _random_hit_case(gpu_lib, oracle_mod, 60_000_000, 103, 13, 5, 0)
         try:
             buf, offs, _ = data_gen.make_reads(104, ref, coff, 1500, 1000, 8000)
             dev = c.aligner.map_batch(buf, offs)
