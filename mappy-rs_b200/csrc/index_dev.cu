@@ -398,7 +398,8 @@ int mmg_index_build_device(int w, int k, int b, int flag, int n_seq, const char 
 	/* table */
 	{
 		uint32_t hb = 4;
-		while (((uint64_t)1 << hb) < n_keys * 4) ++hb;
+		const uint64_t inv_load = getenv("MMG_TABLE_INV_LOAD") ? (uint64_t)atoi(getenv("MMG_TABLE_INV_LOAD")) : 4; /* slots per key (tuning experiment hook) */
+		while (((uint64_t)1 << hb) < n_keys * (inv_load < 2 ? 2 : inv_load)) ++hb;
 		idx->hbits = hb, idx->n_keys = n_keys, idx->n_pos = n_multi;
 		const uint64_t nslots = (uint64_t)1 << hb;
 		const uint32_t big_cap = 1u << 16;
