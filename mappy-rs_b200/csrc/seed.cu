@@ -358,6 +358,7 @@ expand_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint3
 #define AF_MAX_SEEDS 3072
 #define AF_MAX_ANCHORS 65536
 #define AF_MIN_ANCHORS 64
+#define AF_ROUNDS 2             /* hash rounds: each re-tests the survivors of the previous one with another hash */
 #define AF_GATHER 8             /* independent pos[] reads in flight per thread */
 
 /* hashed slot of the position bin (strand, contig, (pos >> shift) + delta) in a table of 2^bits bins */
@@ -448,10 +449,10 @@ anchor_filter_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 		 * gathered ONCE (random 8-byte reads of di.pos are the expensive part) into hit_scratch, in anchor order,
 		 * with the seed's strand in bit 63; everything after that streams through it. */
 		uint32_t n_in = n_full;
-		for (int round = 0; round < 2; ++round) {
-			int bits = 12;
-			while (bits < AF_BIN_BITS && (1u << bits) < 8u * n_in) ++bits;
-			const uint32_t seed = round ? 0x68E31DA4u : 0u;
+		for (int round = 0; round < AF_ROUNDS; ++round) {
+			int bits = 12; /* 32 bins per candidate: ~9 % of the isolated anchors survive a round by collision */
+			while (bits < AF_BIN_BITS && (1u << bits) < 32u * n_in) ++bits;
+			const uint32_t seed = (uint32_t)round * 0x68E31DA4u;
 			for (int j = tid; j < (1 << (bits - 5)); j += AF_THREADS) s_tab[j] = 0, s_two[j] = 0;
 			__syncthreads();
 			if (round == 0) {
