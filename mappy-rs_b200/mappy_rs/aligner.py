@@ -75,21 +75,26 @@ class Mapping:
         return isinstance(o, Mapping) and all(getattr(self, k) == getattr(o, k) for k in self.__slots__)
 
 
-def _mappings_from(res, names, lens, cs_list, md_list, lo, hi):
-    """hits[lo:hi] of a Batch -> list[Mapping] (field mapping of crate minimap2 Aligner::map, lib.rs:493-509)."""
-    out = []
+def _mappings_of_batch(res, names, lens, cs_list, md_list, n_reads):
+    """All hits of a Batch -> per-read lists of Mapping (field mapping of crate minimap2 Aligner::map, lib.rs:493-509).
+    The record arrays are converted column by column (one `tolist()` per field) instead of element by element: at
+    device speed the per-hit Python work is the bottleneck of this host layer."""
     hits, cig = res.hits, res.cigar
-    for i in range(lo, hi):
-        h = hits[i]
-        c0, nc = int(h["cigar_off"]), int(h["n_cigar"])
-        ops = cig[c0:c0 + nc]
-        rid = int(h["rid"])
-        out.append(Mapping(int(h["qs"]), int(h["qe"]), -1 if h["rev"] else 1, names[rid], lens[rid], int(h["rs"]), int(h["re"]),
-                           int(h["mlen"]), int(h["blen"]), int(h["mapq"]), bool(h["is_primary"]),
-                           [(int(x) >> 4, int(x) & 0xf) for x in ops], int(h["nm"]),
-                           md_list[i].decode() if md_list is not None and md_list[i] is not None else None,
-                           cs_list[i].decode() if cs_list is not None and cs_list[i] is not None else None))
-    return out
+    n = len(hits)
+    col = {f: hits[f].tolist() for f in ("qs", "qe", "rev", "rid", "rs", "re", "mlen", "blen", "mapq", "is_primary", "nm", "cigar_off", "n_cigar")}
+    clen, cop = (cig >> 4).tolist(), (cig & 0xf).tolist()
+    out_hits = []
+    for i in range(n):
+        c0, rid = col["cigar_off"][i], col["rid"][i]
+        c1 = c0 + col["n_cigar"][i]
+        md = md_list[i] if md_list is not None else None
+        cs = cs_list[i] if cs_list is not None else None
+        out_hits.append(Mapping(col["qs"][i], col["qe"][i], -1 if col["rev"][i] else 1, names[rid], lens[rid], col["rs"][i], col["re"][i],
+                                col["mlen"][i], col["blen"][i], col["mapq"][i], bool(col["is_primary"][i]),
+                                list(zip(clen[c0:c1], cop[c0:c1])), col["nm"][i],
+                                md.decode() if md is not None else None, cs.decode() if cs is not None else None))
+    ho = res.hit_off.tolist()
+    return [out_hits[ho[i]:ho[i + 1]] for i in range(n_reads)]
 
 
 class AlignmentBatchResultIter:
@@ -222,8 +227,7 @@ class Aligner:
             res = self._aligner.map_batch(buf, offs)
             cs_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 0) if cs else None   # reads the shared pinned buffer
             md_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 1) if md else None
-        ho = res.hit_off
-        return [_mappings_from(res, self._names, self._lens, cs_l, md_l, int(ho[i]), int(ho[i + 1])) for i in range(len(bs))]
+        return _mappings_of_batch(res, self._names, self._lens, cs_l, md_l, len(bs))
 
     def map(self, seq, seq2=None, cs=False, MD=False):
         """Map a single read, blocking (lib.rs:472-514)."""
