@@ -41,7 +41,15 @@ static int aligned_seqs(const mmg_index *idx, const mmg_hit_t *h, const char *se
 	return 0;
 }
 
-static void put_int(std::string &s, long v) { char b[24]; snprintf(b, sizeof(b), "%ld", v); s += b; }
+static void put_int(std::string &s, long v)
+{ /* run lengths: a few digits, written without snprintf (one call per run of matches adds up over a batch) */
+	char b[24];
+	int n = 0;
+	unsigned long u = v < 0 ? 0UL - (unsigned long)v : (unsigned long)v;
+	do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+	if (v < 0) b[n++] = '-';
+	while (n) s += b[--n];
+}
 
 static int gen_cs(const mmg_index *idx, const mmg_hit_t *h, const uint32_t *cigar, const char *seq, int qlen, int no_iden, std::string &s)
 {
@@ -134,11 +142,14 @@ int64_t mmg_gen_tags(const mmg_index *idx, const char *bases, const uint64_t *of
 	std::vector<std::string> out(n_hits);
 	std::atomic<uint32_t> next(0);
 	std::atomic<int> bad(0);
+	if (n_threads < 1) n_threads = 1;
+	uint32_t step = n_reads / (4u * (uint32_t)n_threads); /* reads per claim: small batches still use every thread */
+	step = step < 1 ? 1 : step > 64 ? 64 : step;
 	auto work = [&]() {
 		for (;;) {
-			uint32_t r = next.fetch_add(64);
+			uint32_t r = next.fetch_add(step);
 			if (r >= n_reads) break;
-			for (uint32_t rr = r; rr < r + 64 && rr < n_reads; ++rr) {
+			for (uint32_t rr = r; rr < r + step && rr < n_reads; ++rr) {
 				const char *seq = bases + offsets[rr];
 				const int qlen = (int)(offsets[rr + 1] - offsets[rr]);
 				for (uint64_t i = hit_off[rr]; i < hit_off[rr + 1]; ++i) {
@@ -150,7 +161,6 @@ int64_t mmg_gen_tags(const mmg_index *idx, const char *bases, const uint64_t *of
 			}
 		}
 	};
-	if (n_threads < 1) n_threads = 1;
 	std::vector<std::thread> th;
 	for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
 	work();

@@ -308,19 +308,26 @@ class DeviceAligner:
         return x[:n], y[:n], off
 
 
-def gen_tags(lib, index, buf, offs, res, which, n_threads=4):
+def gen_tags(lib, index, buf, offs, res, which, n_threads=0):
     """cs (which=0) or MD (which=1) strings of every hit of a Batch: list[bytes|None]."""
     n_reads, n_hits = len(offs) - 1, len(res.hits)
     if n_hits == 0:
         return []
+    if n_threads <= 0:
+        n_threads = min(32, os.cpu_count() or 4)
     buf = np.ascontiguousarray(buf, dtype=np.uint8); offs = np.ascontiguousarray(offs, dtype=np.uint64)
     hit_off = np.ascontiguousarray(res.hit_off, dtype=np.uint64)
     hits = np.ascontiguousarray(res.hits); cig = np.ascontiguousarray(res.cigar, dtype=np.uint32)
     so = np.zeros(n_hits + 1, dtype=np.uint64)
     args = [index.h, buf.ctypes.data, offs.ctypes.data, n_reads, hit_off.ctypes.data, hits.ctypes.data, cig.ctypes.data if len(cig) else None, which, n_threads]
-    tot = lib.check(int(lib.L.mmg_gen_tags(*args, None, 0, so.ctypes.data)))
-    out = np.zeros(max(tot, 1), dtype=np.uint8)
-    lib.check(int(lib.L.mmg_gen_tags(*args, out.ctypes.data, tot, so.ctypes.data)))
-    raw = out.tobytes()
-    has = (res.hits["flags"] & 32) != 0
-    return [raw[int(so[i]):int(so[i + 1])] if has[i] else None for i in range(n_hits)]
+    # one call in the common case: a tag is rarely longer than its alignment block; a second call with the exact size otherwise
+    cap = int(hits["blen"].astype(np.int64).sum()) + 64 * n_hits + 1024
+    out = np.empty(cap, dtype=np.uint8)
+    tot = lib.check(int(lib.L.mmg_gen_tags(*args, out.ctypes.data, cap, so.ctypes.data)))
+    if tot > cap:
+        out = np.empty(tot, dtype=np.uint8)
+        lib.check(int(lib.L.mmg_gen_tags(*args, out.ctypes.data, tot, so.ctypes.data)))
+    raw = out[:tot].tobytes()
+    has = ((res.hits["flags"] & 32) != 0).tolist()
+    sl = so.tolist()
+    return [raw[sl[i]:sl[i + 1]] if has[i] else None for i in range(n_hits)]
