@@ -29,14 +29,37 @@ _CIGAR_OPS = "MIDNSHP=X"
 class Mapping:
     """Result of an alignment (lib.rs:106-154).  `cigar` is a list of (length, op) tuples."""
     __slots__ = ("query_start", "query_end", "_strand", "target_name", "target_len", "target_start", "target_end",
-                 "match_len", "block_len", "mapq", "is_primary", "cigar", "NM", "MD", "cs")
+                 "match_len", "block_len", "mapq", "is_primary", "_cigar", "NM", "_MD", "_cs")
+    _FIELDS = ("query_start", "query_end", "_strand", "target_name", "target_len", "target_start", "target_end",
+               "match_len", "block_len", "mapq", "is_primary", "cigar", "NM", "MD", "cs")
 
     def __init__(self, query_start, query_end, strand, target_name, target_len, target_start, target_end,
                  match_len, block_len, mapq, is_primary, cigar, NM, MD, cs):
         self.query_start, self.query_end, self._strand = query_start, query_end, strand
         self.target_name, self.target_len, self.target_start, self.target_end = target_name, target_len, target_start, target_end
         self.match_len, self.block_len, self.mapq, self.is_primary = match_len, block_len, mapq, is_primary
-        self.cigar, self.NM, self.MD, self.cs = cigar, NM, MD, cs
+        # cigar may arrive as a packed uint32 array (len << 4 | op), MD / cs as bytes: they become the list of (len, op)
+        # tuples / str of the reference on first access (building ~10^3 tuples per long read is most of the host time)
+        self._cigar, self.NM, self._MD, self._cs = cigar, NM, MD, cs
+
+    @property
+    def cigar(self):
+        c = self._cigar
+        if not isinstance(c, list):
+            c = self._cigar = list(zip((c >> 4).tolist(), (c & 0xf).tolist()))
+        return c
+
+    @property
+    def MD(self):
+        if isinstance(self._MD, bytes):
+            self._MD = self._MD.decode()
+        return self._MD
+
+    @property
+    def cs(self):
+        if isinstance(self._cs, bytes):
+            self._cs = self._cs.decode()
+        return self._cs
 
     # mappy-style aliases (lib.rs:196-284)
     ctg = property(lambda s: s.target_name)
@@ -72,7 +95,7 @@ class Mapping:
         return "Mapping {\n" + "".join("    %s: %s,\n" % kv for kv in f) + "}"
 
     def __eq__(self, o):
-        return isinstance(o, Mapping) and all(getattr(self, k) == getattr(o, k) for k in self.__slots__)
+        return isinstance(o, Mapping) and all(getattr(self, k) == getattr(o, k) for k in self._FIELDS)
 
 
 def _mappings_of_batch(res, names, lens, cs_list, md_list, n_reads):
@@ -82,7 +105,6 @@ def _mappings_of_batch(res, names, lens, cs_list, md_list, n_reads):
     hits, cig = res.hits, res.cigar
     n = len(hits)
     col = {f: hits[f].tolist() for f in ("qs", "qe", "rev", "rid", "rs", "re", "mlen", "blen", "mapq", "is_primary", "nm", "cigar_off", "n_cigar")}
-    clen, cop = (cig >> 4).tolist(), (cig & 0xf).tolist()
     out_hits = []
     for i in range(n):
         c0, rid = col["cigar_off"][i], col["rid"][i]
@@ -91,8 +113,7 @@ def _mappings_of_batch(res, names, lens, cs_list, md_list, n_reads):
         cs = cs_list[i] if cs_list is not None else None
         out_hits.append(Mapping(col["qs"][i], col["qe"][i], -1 if col["rev"][i] else 1, names[rid], lens[rid], col["rs"][i], col["re"][i],
                                 col["mlen"][i], col["blen"][i], col["mapq"][i], bool(col["is_primary"][i]),
-                                list(zip(clen[c0:c1], cop[c0:c1])), col["nm"][i],
-                                md.decode() if md is not None else None, cs.decode() if cs is not None else None))
+                                cig[c0:c1], col["nm"][i], md, cs))
     ho = res.hit_off.tolist()
     return [out_hits[ho[i]:ho[i + 1]] for i in range(n_reads)]
 
