@@ -547,73 +547,6 @@ __device__ __forceinline__ void ext_dpmem_set(DpMem &m, unsigned char *base, int
 	m.sf = (uint8_t*)(m.s + T16);
 }
 
-/* ---- two cells per 32-bit word (16-bit fields) ----
- * The recurrence of one cell is ~45 scalar integer operations.  sm_100a has single-instruction 16x2 max / add-max
- * (VIMNMX3.U16x2, VIADDMNMX.S16x2), so the core loop keeps two cells in one register: every quantity is held in a
- * 16-bit field with a bias that keeps it non-negative, plain 32-bit adds then act on both fields at once (no carry
- * can cross a field).  The arg-max direction rides in the low three bits of the compared values (value*8 + priority:
- * "first maximum wins" for left-aligned gaps, "last maximum wins" for right-aligned ones, as the > / >= comparisons
- * of ksw2_extd2_sse.c resolve ties), and the four "gap continues" bits are read off one carry bit per term. */
-#ifdef MMG_EMU
-static inline uint32_t dp_prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-	const uint64_t v = (uint64_t)b << 32 | a;
-	uint32_t r = 0;
-	for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
-	return r;
-}
-static inline uint32_t dp_f2(uint32_t lo, uint32_t hi) { return (lo & 0xffffu) | hi << 16; }
-static inline uint32_t dp_max3u(uint32_t a, uint32_t b, uint32_t c)
-{
-	auto mx = [](uint32_t x, uint32_t y) { return x > y ? x : y; };
-	return dp_f2(mx(mx(a & 0xffff, b & 0xffff), c & 0xffff), mx(mx(a >> 16, b >> 16), c >> 16));
-}
-static inline uint32_t dp_minu(uint32_t a, uint32_t b) { return dp_f2((a & 0xffff) < (b & 0xffff) ? a : b, (a >> 16) < (b >> 16) ? a >> 16 : b >> 16); }
-static inline uint32_t dp_addmaxs(uint32_t a, uint32_t b, uint32_t c)
-{
-	auto f = [](uint32_t x, uint32_t y, uint32_t z) { int16_t s = (int16_t)(uint16_t)(x + y), m = (int16_t)(uint16_t)z; return (uint32_t)(uint16_t)(s > m ? s : m); };
-	return dp_f2(f(a & 0xffff, b & 0xffff, c & 0xffff), f(a >> 16, b >> 16, c >> 16));
-}
-#else
-__device__ __forceinline__ uint32_t dp_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
-__device__ __forceinline__ uint32_t dp_max3u(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
-__device__ __forceinline__ uint32_t dp_minu(uint32_t a, uint32_t b) { return __vminu2(a, b); }
-__device__ __forceinline__ uint32_t dp_addmaxs(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
-#endif
-#define DP_W(c) ((uint32_t)(c) * 0x00010001u)          /* the same 16-bit value in both fields */
-#define DP_LD32(p) (*(const uint32_t*)(p))
-#define DP_ST32(p, v) (*(uint32_t*)(p) = (v))
-
-/* constants of one pass (all uniform) */
-struct DpK {
-	uint32_t p_s, p_a, p_b, p_a2, p_b2;     /* value*8 + priority addends (the score term also carries its extra bias) */
-	uint32_t d_flip;                         /* direction = d_flip - priority (left) or priority (right) */
-	uint32_t zcap;                           /* sc_mch + 256 */
-	uint32_t fa, fb, fa2, fb2;               /* addends that put "term > 0" (left) / "term >= 0" (right) in bits 12..15 */
-	uint32_t ra, rb, ra2, rb2;               /* re-bias of the clamped terms (signed 16-bit fields) */
-	uint32_t floor1, floor2;                 /* 128 - qe, 128 - qe2 */
-	bool right;
-};
-
-/* One 16x2 word: two cells.  Inputs are biased by 128 (S, U, Y, Y2 of the cell; Xs, Vs, X2s of its left neighbour).
- * Outputs: the six new array values (biased by 128, low byte of each field) and the traceback byte. */
-__device__ __forceinline__ void dp_cell2(const DpK &k, uint32_t S, uint32_t U, uint32_t Y, uint32_t Y2, uint32_t Xs, uint32_t Vs, uint32_t X2s,
-                                         uint32_t &nu, uint32_t &nv, uint32_t &nx, uint32_t &ny, uint32_t &nx2, uint32_t &ny2, uint32_t &nd)
-{
-	const uint32_t A = Xs + Vs, B = Y + U, A2 = X2s + Vs, B2 = Y2 + U;                 /* term + 256 */
-	const uint32_t M = dp_max3u(dp_max3u(S * 8 + k.p_s, A * 8 + k.p_a, B * 8 + k.p_b), A2 * 8 + k.p_a2, B2 * 8 + k.p_b2);
-	const uint32_t pr = M & 0x00070007u;
-	const uint32_t z = dp_minu((M >> 3) & 0x1fff1fffu, k.zcap);                        /* z + 256 */
-	nd = k.right ? pr : k.d_flip - pr;
-	nu = z - Vs, nv = z - U;                                                           /* (z - v[t-1]) + 128, (z - u[t]) + 128 */
-	const uint32_t Fa = A - z + k.fa, Fb = B - z + k.fb, Fa2 = A2 - z + k.fa2, Fb2 = B2 - z + k.fb2;
-	nx = dp_addmaxs(Fa, k.ra, k.floor1), ny = dp_addmaxs(Fb, k.rb, k.floor1);
-	nx2 = dp_addmaxs(Fa2, k.ra2, k.floor2), ny2 = dp_addmaxs(Fb2, k.rb2, k.floor2);
-	const uint32_t g1 = (Fb2 & 0x80008000u) | (Fa2 & 0x7fff7fffu), g2 = (Fb & 0x20002000u) | (Fa & 0xdfffdfffu);
-	const uint32_t g = (g1 & 0xc000c000u) | (g2 & 0x3fff3fffu);
-	nd |= (g >> 9) & 0x00780078u;
-}
-
 /* One pass of ksw_extd2_sse over (qlen x tlen).  All lanes of the warp call it.  SMEM = true: the job's arrays are
  * the warp's shared-memory slice; the pointers are derived from the shared array inside this function so that the
  * compiler emits shared-memory loads/stores with 32-bit addresses instead of generic ones. */
@@ -640,20 +573,6 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 	int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
 	if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
 	const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
-	/* constants of the packed core (dp_cell2): every term is carried with bias 256, its test constant puts
-	 * "term - z + gap_open > 0" (left-aligned; ">= 0" right-aligned) into bit 12, 13, 14 or 15 of its field */
-	DpK dk;
-	{
-		const int ge = right ? 0 : 1;
-		dk.right = right;
-		dk.p_s = DP_W(128 * 8 + (right ? 0 : 4)), dk.p_a = DP_W(right ? 1 : 3), dk.p_b = DP_W(2), dk.p_a2 = DP_W(right ? 3 : 1), dk.p_b2 = DP_W(right ? 4 : 0);
-		dk.d_flip = DP_W(4), dk.zcap = DP_W(sc_mch + 256);
-		dk.fa = DP_W(q + 4096 - ge), dk.fb = DP_W(q + 8192 - ge), dk.fa2 = DP_W(q2 + 16384 - ge), dk.fb2 = DP_W(q2 + 32768 - ge);
-		dk.ra = DP_W((uint16_t)(128 - qe - (4096 - ge))), dk.rb = DP_W((uint16_t)(128 - qe - (8192 - ge)));
-		dk.ra2 = DP_W((uint16_t)(128 - qe2 - (16384 - ge))), dk.rb2 = DP_W((uint16_t)(128 - qe2 - (32768 - ge)));
-		dk.floor1 = DP_W((uint16_t)(128 - qe)), dk.floor2 = DP_W((uint16_t)(128 - qe2));
-	}
-	const uint32_t sc_b4 = (uint32_t)(sc_mch + 128) * 0x01010101u, scN_b4 = (uint32_t)(sc_N + 128) * 0x01010101u;
 	/* ksw_reset_extz */
 	int32_t ez_max = 0, ez_score = KSW_NEG_INF, ez_mqe = KSW_NEG_INF, ez_mte = KSW_NEG_INF;
 	int ez_max_q = -1, ez_max_t = -1, ez_mqe_t = -1, ez_mte_q = -1, zdropped = 0, reach_end = 0;
@@ -691,60 +610,84 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 			m.y[r] = (int8_t)(-q - e), m.y2[r] = (int8_t)(-q2 - e2);
 			m.u[r] = (int8_t)(r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2);
 		}
-		/* scores: upstream stores 16 lanes at a time starting at st0 (lanes past en0 included; bytes below st0 keep
-		 * their old value, which the 16-aligned core below does read).  Four bases per lane: one aligned word of the
-		 * target, the query bytes through a funnel of two aligned words, byte-parallel compare. */
+		/* scores: upstream stores 16 lanes at a time starting at st0 (lanes past en0 included) */
 		{
-			const int lim = st0 + ((en0 - st0) / 16 + 1) * 16 < T16 ? st0 + ((en0 - st0) / 16 + 1) * 16 : T16;
-			const int qoff = T16 + (qlen - 1 - r);           /* qrr = qr + (qlen-1-r), qr = sf + T16 */
-			const uint32_t qsel = 0x3210u + 0x1111u * (uint32_t)(qoff & 3);
-			for (int t4 = (st0 & ~3) + 4 * lane; t4 < lim; t4 += 128) {
-				const uint32_t tw = DP_LD32(m.sf + t4);
-				const int qa = (qoff + t4) & ~3;
-				const uint32_t qlo = DP_LD32(m.sf + qa), qhi = qa + 4 < m.flat_sz ? DP_LD32(m.sf + qa + 4) : 0u;
-				const uint32_t qw = dp_prmt(qlo, qhi, qsel);
-				const uint32_t nz = (((tw ^ qw) + 0x7f7f7f7fu) >> 7) & 0x01010101u;            /* 1 where the bases differ */
-				const uint32_t isn = (((tw | qw) >> 2) & 0x01010101u) * 0xffu;                  /* 0xff where either is N */
-				uint32_t sb = sc_b4 - nz * (uint32_t)(sc_mch - sc_mis);
-				sb = ((sb & ~isn) | (scN_b4 & isn)) ^ 0x80808080u;
-				const int lo = st0 - t4, hi = lim - t4;
-				if (lo > 0 || hi < 4) {
-					const uint32_t vm = (hi >= 4 ? 0xffffffffu : (1u << 8 * hi) - 1) & ~(lo <= 0 ? 0u : (1u << 8 * lo) - 1);
-					sb = (sb & vm) | (DP_LD32(m.s + t4) & ~vm);
+			const int n_set = ((en0 - st0) / 16 + 1) * 16, qoff = T16 + (qlen - 1 - r); /* qrr = qr + (qlen-1-r), qr = sf + T16 */
+			for (int i = lane; i < n_set; i += 32) {
+				const int t = st0 + i;
+				if (t < T16) {
+					const int is = t, iq = qoff + t;
+					const int sq = is < m.flat_sz ? m.sf[is] : 0, sq2 = (iq >= 0 && iq < m.flat_sz) ? m.sf[iq] : 0;
+					int sc = sq == sq2 ? sc_mch : sc_mis;
+					if (sq == 4 || sq2 == 4) sc = sc_N;
+					m.s[t] = (int8_t)sc;
 				}
-				DP_ST32(m.s + t4, sb);
 			}
 		}
 		__syncwarp();
-		/* core: chunks of 128 cells (four per lane, as two 16x2 words) from high t to low t; every load of a chunk
-		 * precedes its stores, so a cell reads its left neighbour's OLD x/v/x2 */
+		/* core: chunks of 32 cells from high t to low t (a cell reads its left neighbour's OLD x/v/x2) */
 		uint8_t *pr = tb + (size_t)r * n_col - st;
-		for (int base = st + ((en - st) >> 7 << 7); base >= st; base -= 128) {
-			const int t = base + 4 * lane;
+		for (int base = st + ((en - st) >> 5 << 5); base >= st; base -= 32) {
+			const int t = base + lane;
 			const bool act = t <= en;
-			uint32_t sw = 0, uw = 0, yw = 0, y2w = 0, xs = 0, vs = 0, x2s = 0;
+			int z = 0, a = 0, b = 0, a2 = 0, b2 = 0, vt1 = 0, ut = 0;
 			if (act) {
-				sw = DP_LD32(m.s + t) ^ 0x80808080u, uw = DP_LD32(m.u + t) ^ 0x80808080u;
-				yw = DP_LD32(m.y + t) ^ 0x80808080u, y2w = DP_LD32(m.y2 + t) ^ 0x80808080u;
-				const uint32_t xp = t == st ? (uint32_t)x1 << 24 : DP_LD32(m.x + t - 4), vp = t == st ? (uint32_t)v1 << 24 : DP_LD32(m.v + t - 4);
-				const uint32_t x2p = t == st ? (uint32_t)x21 << 24 : DP_LD32(m.x2 + t - 4);
-				xs = dp_prmt(xp, DP_LD32(m.x + t), 0x6543) ^ 0x80808080u;      /* x[t-1 .. t+2] */
-				vs = dp_prmt(vp, DP_LD32(m.v + t), 0x6543) ^ 0x80808080u;
-				x2s = dp_prmt(x2p, DP_LD32(m.x2 + t), 0x6543) ^ 0x80808080u;
+				z = m.s[t];
+				const int xt1 = t == st ? x1 : m.x[t - 1];
+				vt1 = t == st ? v1 : m.v[t - 1];
+				const int x2t1 = t == st ? x21 : m.x2[t - 1];
+				ut = m.u[t];
+				a = xt1 + vt1, b = m.y[t] + ut, a2 = x2t1 + vt1, b2 = m.y2[t] + ut;
 			}
 			__syncwarp();
 			if (act) {
-				uint32_t nu[2], nv[2], nx[2], ny[2], nx2[2], ny2[2], nd[2];
-#pragma unroll
-				for (int h = 0; h < 2; ++h) {
-					const uint32_t sel = h ? 0x4342u : 0x4140u;               /* bytes (0,1) or (2,3) into the two fields */
-					dp_cell2(dk, dp_prmt(sw, 0, sel), dp_prmt(uw, 0, sel), dp_prmt(yw, 0, sel), dp_prmt(y2w, 0, sel),
-					         dp_prmt(xs, 0, sel), dp_prmt(vs, 0, sel), dp_prmt(x2s, 0, sel), nu[h], nv[h], nx[h], ny[h], nx2[h], ny2[h], nd[h]);
+				int d;
+				if (!right) {
+					d = a > z ? 1 : 0;
+					z = z > a ? z : a;
+					d = b > z ? 2 : d;
+					z = z > b ? z : b;
+					d = a2 > z ? 3 : d;
+					z = z > a2 ? z : a2;
+					d = b2 > z ? 4 : d;
+					z = z > b2 ? z : b2;
+				} else {
+					d = z > a ? 0 : 1;
+					z = z > a ? z : a;
+					d = z > b ? d : 2;
+					z = z > b ? z : b;
+					d = z > a2 ? d : 3;
+					z = z > a2 ? z : a2;
+					d = z > b2 ? d : 4;
+					z = z > b2 ? z : b2;
 				}
-				DP_ST32(m.u + t, dp_prmt(nu[0], nu[1], 0x6420) ^ 0x80808080u), DP_ST32(m.v + t, dp_prmt(nv[0], nv[1], 0x6420) ^ 0x80808080u);
-				DP_ST32(m.x + t, dp_prmt(nx[0], nx[1], 0x6420) ^ 0x80808080u), DP_ST32(m.y + t, dp_prmt(ny[0], ny[1], 0x6420) ^ 0x80808080u);
-				DP_ST32(m.x2 + t, dp_prmt(nx2[0], nx2[1], 0x6420) ^ 0x80808080u), DP_ST32(m.y2 + t, dp_prmt(ny2[0], ny2[1], 0x6420) ^ 0x80808080u);
-				DP_ST32(pr + t, dp_prmt(nd[0], nd[1], 0x6420));
+				z = z < sc_mch ? z : sc_mch;
+				m.u[t] = (int8_t)(z - vt1);
+				m.v[t] = (int8_t)(z - ut);
+				int tmp = z - q;
+				a -= tmp, b -= tmp;
+				tmp = z - q2;
+				a2 -= tmp, b2 -= tmp;
+				if (!right) {
+					m.x[t] = (int8_t)((a > 0 ? a : 0) - qe);
+					d |= a > 0 ? 0x08 : 0;
+					m.y[t] = (int8_t)((b > 0 ? b : 0) - qe);
+					d |= b > 0 ? 0x10 : 0;
+					m.x2[t] = (int8_t)((a2 > 0 ? a2 : 0) - qe2);
+					d |= a2 > 0 ? 0x20 : 0;
+					m.y2[t] = (int8_t)((b2 > 0 ? b2 : 0) - qe2);
+					d |= b2 > 0 ? 0x40 : 0;
+				} else {
+					m.x[t] = (int8_t)((0 > a ? 0 : a) - qe);
+					d |= 0 > a ? 0 : 0x08;
+					m.y[t] = (int8_t)((0 > b ? 0 : b) - qe);
+					d |= 0 > b ? 0 : 0x10;
+					m.x2[t] = (int8_t)((0 > a2 ? 0 : a2) - qe2);
+					d |= 0 > a2 ? 0 : 0x20;
+					m.y2[t] = (int8_t)((0 > b2 ? 0 : b2) - qe2);
+					d |= 0 > b2 ? 0 : 0x40;
+				}
+				pr[t] = (uint8_t)d;
 			}
 			__syncwarp();
 		}
