@@ -521,11 +521,26 @@ ext_job_scan_kernel(ExtBufs xb, uint32_t j0, uint32_t j1)
 
 /* ---------- the DP ---------- */
 struct DpMem {
-	int8_t *u, *v, *x, *y, *x2, *y2, *s;
-	uint8_t *sf;            /* target, then (contiguous) the reversed query, as in upstream's single kcalloc block */
 	int32_t *H;
+	uint32_t *ga, *gb, *gc; /* the six difference arrays, 16-bit fields biased by 128, one 16-byte record per four columns:
+	                         * ga = (u01, u23, y01, y23), gb = (x01, v01, x23, v23), gc = (x2_01, x2_23, y2_01, y2_23) */
+	uint8_t *s;             /* match scores, bytes biased by 128 */
+	uint8_t *sf;            /* target, then (contiguous) the reversed query, as in upstream's single kcalloc block */
 	int T16, flat_sz;       /* flat_sz = bytes addressable from sf (T16 + Q16 + 16) */
 };
+#define EXT_DP_BYTES(T16, Q16) ((size_t)18 * (T16) + (Q16) + 16)   /* H 4, ga/gb/gc 4 each, s 1, target 1 per column */
+
+/* scalar views of the packed arrays (boundary cells, the H bookkeeping) */
+enum { DP_U, DP_Y, DP_X, DP_V, DP_X2, DP_Y2 };
+__device__ __forceinline__ uint16_t *dp_field(const DpMem &m, int a, int t)
+{
+	const int h = (t >> 1) & 1;
+	uint32_t *g = a == DP_U || a == DP_Y ? m.ga : a == DP_X || a == DP_V ? m.gb : m.gc;
+	const int word = a == DP_U || a == DP_X2 ? h : a == DP_Y || a == DP_Y2 ? 2 + h : a == DP_X ? 2 * h : 2 * h + 1;
+	return (uint16_t*)(g + (size_t)(t >> 2) * 4 + word) + (t & 1);
+}
+__device__ __forceinline__ int dp_get(const DpMem &m, int a, int t) { return (int)*dp_field(m, a, t) - 128; }
+__device__ __forceinline__ void dp_set(const DpMem &m, int a, int t, int v) { *dp_field(m, a, t) = (uint16_t)(v + 128); }
 
 __device__ __forceinline__ bool ez_apply_zdrop(int32_t *ez_max, int *ez_max_t, int *ez_max_q, int32_t H, int r, int t, int zdrop, int e)
 { /* ksw2.h ksw_apply_zdrop with is_rot = 1 */
@@ -543,8 +558,9 @@ __device__ __forceinline__ void ext_dpmem_set(DpMem &m, unsigned char *base, int
 {
 	m.T16 = T16, m.flat_sz = T16 + Q16 + 16;
 	m.H = (int32_t*)base;
-	m.u = (int8_t*)(base + (size_t)4 * T16), m.v = m.u + T16, m.x = m.v + T16, m.y = m.x + T16, m.x2 = m.y + T16, m.y2 = m.x2 + T16, m.s = m.y2 + T16;
-	m.sf = (uint8_t*)(m.s + T16);
+	m.ga = (uint32_t*)(base + (size_t)4 * T16), m.gb = m.ga + T16, m.gc = m.gb + T16;
+	m.s = (uint8_t*)(m.gc + T16);
+	m.sf = m.s + T16;
 }
 
 /* ---- two cells per 32-bit word (16-bit fields) ----
@@ -580,6 +596,8 @@ __device__ __forceinline__ uint32_t dp_max3u(uint32_t a, uint32_t b, uint32_t c)
 __device__ __forceinline__ uint32_t dp_minu(uint32_t a, uint32_t b) { return __vminu2(a, b); }
 __device__ __forceinline__ uint32_t dp_addmaxs(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 #endif
+struct alignas(16) DpQuad { uint32_t x, y, z, w; };
+struct alignas(8) DpPair { uint32_t x, y; };
 #define DP_W(c) ((uint32_t)(c) * 0x00010001u)          /* the same 16-bit value in both fields */
 #define DP_LD32(p) (*(const uint32_t*)(p))
 #define DP_ST32(p, v) (*(uint32_t*)(p) = (v))
@@ -596,7 +614,7 @@ struct DpK {
 };
 
 /* One 16x2 word: two cells.  Inputs are biased by 128 (S, U, Y, Y2 of the cell; Xs, Vs, X2s of its left neighbour).
- * Outputs: the six new array values (biased by 128, low byte of each field) and the traceback byte. */
+ * Outputs: the six new array values (fields biased by 128) and the traceback byte. */
 __device__ __forceinline__ void dp_cell2(const DpK &k, uint32_t S, uint32_t U, uint32_t Y, uint32_t Y2, uint32_t Xs, uint32_t Vs, uint32_t X2s,
                                          uint32_t &nu, uint32_t &nv, uint32_t &nx, uint32_t &ny, uint32_t &nx2, uint32_t &ny2, uint32_t &nd)
 {
@@ -658,11 +676,15 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 	int32_t ez_max = 0, ez_score = KSW_NEG_INF, ez_mqe = KSW_NEG_INF, ez_mte = KSW_NEG_INF;
 	int ez_max_q = -1, ez_max_t = -1, ez_mqe_t = -1, ez_mte_q = -1, zdropped = 0, reach_end = 0;
 	/* NB: mm_align_pair never calls the kernel with scores that make -min_sc > 2*(q+e) on this path */
-	for (int i = lane; i < T16; i += 32) {
-		m.u[i] = m.v[i] = m.x[i] = m.y[i] = (int8_t)(-q - e);
-		m.x2[i] = m.y2[i] = (int8_t)(-q2 - e2);
-		m.s[i] = 0;
-		if (!approx_max) m.H[i] = KSW_NEG_INF;
+	{
+		const uint32_t g1 = DP_W(128 - q - e), g2 = DP_W(128 - q2 - e2);
+		for (int g = lane; g < T16 >> 2; g += 32) {
+			uint32_t *a = m.ga + 4 * g, *b = m.gb + 4 * g, *c = m.gc + 4 * g;
+			a[0] = a[1] = a[2] = a[3] = g1, b[0] = b[1] = b[2] = b[3] = g1;
+			c[0] = c[1] = c[2] = c[3] = g2;
+			DP_ST32(m.s + 4 * g, 0x80808080u);
+			if (!approx_max) m.H[4 * g] = m.H[4 * g + 1] = m.H[4 * g + 2] = m.H[4 * g + 3] = KSW_NEG_INF;
+		}
 	}
 	__syncwarp();
 	int32_t H0 = 0;
@@ -678,73 +700,62 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 		if (st > en) { zdropped = 1; break; }
 		st0 = st, en0 = en;
 		st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;
-		int x1, x21, v1;
-		if (st > 0) {
-			if (st - 1 >= last_st && st - 1 <= last_en) x1 = m.x[st - 1], x21 = m.x2[st - 1], v1 = m.v[st - 1];
-			else x1 = -q - e, x21 = -q2 - e2, v1 = -q - e;
-		} else {
-			x1 = -q - e, x21 = -q2 - e2;
-			v1 = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
-		}
+		const int bnd = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
+		int x1 = -q - e, x21 = -q2 - e2, v1 = st > 0 ? -q - e : bnd;
+		if (st > 0 && st - 1 >= last_st && st - 1 <= last_en) x1 = dp_get(m, DP_X, st - 1), x21 = dp_get(m, DP_X2, st - 1), v1 = dp_get(m, DP_V, st - 1);
 		__syncwarp();
-		if (en >= r && lane == 0) {
-			m.y[r] = (int8_t)(-q - e), m.y2[r] = (int8_t)(-q2 - e2);
-			m.u[r] = (int8_t)(r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2);
-		}
-		/* scores: upstream stores 16 lanes at a time starting at st0 (lanes past en0 included; bytes below st0 keep
-		 * their old value, which the 16-aligned core below does read).  Four bases per lane: one aligned word of the
-		 * target, the query bytes through a funnel of two aligned words, byte-parallel compare. */
-		{
-			const int lim = st0 + ((en0 - st0) / 16 + 1) * 16 < T16 ? st0 + ((en0 - st0) / 16 + 1) * 16 : T16;
-			const int qoff = T16 + (qlen - 1 - r);           /* qrr = qr + (qlen-1-r), qr = sf + T16 */
-			const uint32_t qsel = 0x3210u + 0x1111u * (uint32_t)(qoff & 3);
-			for (int t4 = (st0 & ~3) + 4 * lane; t4 < lim; t4 += 128) {
-				const uint32_t tw = DP_LD32(m.sf + t4);
-				const int qa = (qoff + t4) & ~3;
+		if (en >= r && lane < 3) dp_set(m, lane == 0 ? DP_Y : lane == 1 ? DP_Y2 : DP_U, r, lane == 0 ? -q - e : lane == 1 ? -q2 - e2 : bnd);
+		__syncwarp();
+		/* One sweep per 128 columns (four per lane, as two 16x2 words), from high t to low t.
+		 * Scores: upstream stores 16 lanes at a time starting at st0 (lanes past en0 included; bytes below st0 keep
+		 * their old value, which the 16-aligned core does read): one aligned word of the target, the query bytes
+		 * through a funnel of two aligned words, byte-parallel compare, merged into the lane's own word of s[].
+		 * Core: every load of a sweep precedes its stores, so a cell reads its left neighbour's OLD x/v/x2. */
+		const int lim = st0 + ((en0 - st0) / 16 + 1) * 16 < T16 ? st0 + ((en0 - st0) / 16 + 1) * 16 : T16;
+		const int qoff = T16 + (qlen - 1 - r);               /* qrr = qr + (qlen-1-r), qr = sf + T16 */
+		const uint32_t qsel = 0x3210u + 0x1111u * (uint32_t)(qoff & 3);
+		const int top = en > lim - 1 ? en : lim - 1;
+		uint8_t *pr = tb + (size_t)r * n_col - st;
+		for (int base = st + ((top - st) >> 7 << 7); base >= st; base -= 128) {
+			const int t = base + 4 * lane;
+			const bool act = t <= en, sact = t < lim && t + 4 > st0;
+			uint32_t sw = 0, A0, A1, A2, A3, B0, B1, B2, B3, C0, C1, C2, C3, xp, vp, x2p;   /* only read where act */
+			if (sact) {
+				const uint32_t tw = DP_LD32(m.sf + t);
+				const int qa = (qoff + t) & ~3;
 				const uint32_t qlo = DP_LD32(m.sf + qa), qhi = qa + 4 < m.flat_sz ? DP_LD32(m.sf + qa + 4) : 0u;
 				const uint32_t qw = dp_prmt(qlo, qhi, qsel);
 				const uint32_t nz = (((tw ^ qw) + 0x7f7f7f7fu) >> 7) & 0x01010101u;            /* 1 where the bases differ */
 				const uint32_t isn = (((tw | qw) >> 2) & 0x01010101u) * 0xffu;                  /* 0xff where either is N */
-				uint32_t sb = sc_b4 - nz * (uint32_t)(sc_mch - sc_mis);
-				sb = ((sb & ~isn) | (scN_b4 & isn)) ^ 0x80808080u;
-				const int lo = st0 - t4, hi = lim - t4;
+				sw = sc_b4 - nz * (uint32_t)(sc_mch - sc_mis);
+				sw = (sw & ~isn) | (scN_b4 & isn);
+				const int lo = st0 - t, hi = lim - t;
 				if (lo > 0 || hi < 4) {
 					const uint32_t vm = (hi >= 4 ? 0xffffffffu : (1u << 8 * hi) - 1) & ~(lo <= 0 ? 0u : (1u << 8 * lo) - 1);
-					sb = (sb & vm) | (DP_LD32(m.s + t4) & ~vm);
+					sw = (sw & vm) | (DP_LD32(m.s + t) & ~vm);
 				}
-				DP_ST32(m.s + t4, sb);
-			}
-		}
-		__syncwarp();
-		/* core: chunks of 128 cells (four per lane, as two 16x2 words) from high t to low t; every load of a chunk
-		 * precedes its stores, so a cell reads its left neighbour's OLD x/v/x2 */
-		uint8_t *pr = tb + (size_t)r * n_col - st;
-		for (int base = st + ((en - st) >> 7 << 7); base >= st; base -= 128) {
-			const int t = base + 4 * lane;
-			const bool act = t <= en;
-			uint32_t sw = 0, uw = 0, yw = 0, y2w = 0, xs = 0, vs = 0, x2s = 0;
+				DP_ST32(m.s + t, sw);
+			} else if (act) sw = DP_LD32(m.s + t);
 			if (act) {
-				sw = DP_LD32(m.s + t) ^ 0x80808080u, uw = DP_LD32(m.u + t) ^ 0x80808080u;
-				yw = DP_LD32(m.y + t) ^ 0x80808080u, y2w = DP_LD32(m.y2 + t) ^ 0x80808080u;
-				const uint32_t xp = t == st ? (uint32_t)x1 << 24 : DP_LD32(m.x + t - 4), vp = t == st ? (uint32_t)v1 << 24 : DP_LD32(m.v + t - 4);
-				const uint32_t x2p = t == st ? (uint32_t)x21 << 24 : DP_LD32(m.x2 + t - 4);
-				xs = dp_prmt(xp, DP_LD32(m.x + t), 0x6543) ^ 0x80808080u;      /* x[t-1 .. t+2] */
-				vs = dp_prmt(vp, DP_LD32(m.v + t), 0x6543) ^ 0x80808080u;
-				x2s = dp_prmt(x2p, DP_LD32(m.x2 + t), 0x6543) ^ 0x80808080u;
+				const DpQuad a = *(const DpQuad*)(m.ga + t), b = *(const DpQuad*)(m.gb + t), c = *(const DpQuad*)(m.gc + t);
+				A0 = a.x, A1 = a.y, A2 = a.z, A3 = a.w, B0 = b.x, B1 = b.y, B2 = b.z, B3 = b.w, C0 = c.x, C1 = c.y, C2 = c.z, C3 = c.w;
+				if (t == st) xp = (uint32_t)(x1 + 128) << 16, vp = (uint32_t)(v1 + 128) << 16, x2p = (uint32_t)(x21 + 128) << 16;
+				else {
+					const DpPair pb = *(const DpPair*)(m.gb + t - 2);
+					xp = pb.x, vp = pb.y, x2p = m.gc[t - 3];
+				}
 			}
 			__syncwarp();
 			if (act) {
-				uint32_t nu[2], nv[2], nx[2], ny[2], nx2[2], ny2[2], nd[2];
-#pragma unroll
-				for (int h = 0; h < 2; ++h) {
-					const uint32_t sel = h ? 0x4342u : 0x4140u;               /* bytes (0,1) or (2,3) into the two fields */
-					dp_cell2(dk, dp_prmt(sw, 0, sel), dp_prmt(uw, 0, sel), dp_prmt(yw, 0, sel), dp_prmt(y2w, 0, sel),
-					         dp_prmt(xs, 0, sel), dp_prmt(vs, 0, sel), dp_prmt(x2s, 0, sel), nu[h], nv[h], nx[h], ny[h], nx2[h], ny2[h], nd[h]);
-				}
-				DP_ST32(m.u + t, dp_prmt(nu[0], nu[1], 0x6420) ^ 0x80808080u), DP_ST32(m.v + t, dp_prmt(nv[0], nv[1], 0x6420) ^ 0x80808080u);
-				DP_ST32(m.x + t, dp_prmt(nx[0], nx[1], 0x6420) ^ 0x80808080u), DP_ST32(m.y + t, dp_prmt(ny[0], ny[1], 0x6420) ^ 0x80808080u);
-				DP_ST32(m.x2 + t, dp_prmt(nx2[0], nx2[1], 0x6420) ^ 0x80808080u), DP_ST32(m.y2 + t, dp_prmt(ny2[0], ny2[1], 0x6420) ^ 0x80808080u);
-				DP_ST32(pr + t, dp_prmt(nd[0], nd[1], 0x6420));
+				uint32_t nu0, nv0, nx0, ny0, nx20, ny20, nd0, nu1, nv1, nx1, ny1, nx21, ny21, nd1;
+				dp_cell2(dk, dp_prmt(sw, 0, 0x4140), A0, A2, C2, __funnelshift_l(xp, B0, 16), __funnelshift_l(vp, B1, 16), __funnelshift_l(x2p, C0, 16),
+				         nu0, nv0, nx0, ny0, nx20, ny20, nd0);
+				dp_cell2(dk, dp_prmt(sw, 0, 0x4342), A1, A3, C3, __funnelshift_l(B0, B2, 16), __funnelshift_l(B1, B3, 16), __funnelshift_l(C0, C1, 16),
+				         nu1, nv1, nx1, ny1, nx21, ny21, nd1);
+				DpQuad a, b, c;
+				a.x = nu0, a.y = nu1, a.z = ny0, a.w = ny1, b.x = nx0, b.y = nv0, b.z = nx1, b.w = nv1, c.x = nx20, c.y = nx21, c.z = ny20, c.w = ny21;
+				*(DpQuad*)(m.ga + t) = a, *(DpQuad*)(m.gb + t) = b, *(DpQuad*)(m.gc + t) = c;
+				DP_ST32(pr + t, dp_prmt(nd0, nd1, 0x6420));
 			}
 			__syncwarp();
 		}
@@ -753,12 +764,12 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 			int32_t max_H, max_t;
 			if (r > 0) {
 				const int en1 = st0 + (en0 - st0) / 4 * 4;
-				int32_t hen = en0 > 0 ? m.H[en0 - 1] + m.u[en0] : m.H[en0] + m.v[en0];
+				int32_t hen = en0 > 0 ? m.H[en0 - 1] + dp_get(m, DP_U, en0) : m.H[en0] + dp_get(m, DP_V, en0);
 				__syncwarp();
 				/* H[t] += v[t] for t in [st0, en0); upstream's 4-lane SSE max followed by a scalar tail */
 				long long kg = -1, kr = -1; /* (value, tie) keys; larger wins */
 				for (int t = st0 + lane; t < en0; t += 32) {
-					int32_t h = m.H[t] + m.v[t];
+					int32_t h = m.H[t] + dp_get(m, DP_V, t);
 					m.H[t] = h;
 					if (t < en1) { /* group region: value, then SSE lane (t-st0)&3 ascending, then t ascending */
 						long long k = ((long long)h - KSW_NEG_INF) << 28 | (long long)(3 - ((t - st0) & 3)) << 26 | (long long)(0x3ffffff - t);
@@ -786,7 +797,7 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 				}
 				__syncwarp();
 			} else {
-				max_H = m.v[0] - qe, max_t = 0;
+				max_H = dp_get(m, DP_V, 0) - qe, max_t = 0;
 				__syncwarp();
 				if (lane == 0) m.H[0] = max_H;
 				__syncwarp();
@@ -799,58 +810,89 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 		} else {
 			if (r > 0) {
 				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
-					int32_t d0 = m.v[last_H0_t], d1 = m.u[last_H0_t + 1];
+					int32_t d0 = dp_get(m, DP_V, last_H0_t), d1 = dp_get(m, DP_U, last_H0_t + 1);
 					if (d0 > d1) H0 += d0;
 					else H0 += d1, ++last_H0_t;
 				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
-					H0 += m.v[last_H0_t];
+					H0 += dp_get(m, DP_V, last_H0_t);
 				} else {
-					++last_H0_t, H0 += m.u[last_H0_t];
+					++last_H0_t, H0 += dp_get(m, DP_U, last_H0_t);
 				}
-			} else H0 = m.v[0] - qe, last_H0_t = 0;
+			} else H0 = dp_get(m, DP_V, 0) - qe, last_H0_t = 0;
 			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H0;
 		}
 		last_st = st, last_en = en;
 	}
 	__syncwarp();
-	/* ---- backtrack (ksw_backtrack, is_rot = 1) on lane 0 ---- */
+	/* ---- backtrack (ksw_backtrack, is_rot = 1) ----
+	 * The walk is serial, and one traceback byte per step straight from global memory costs a full L2 round trip
+	 * per CIGAR base.  The warp therefore fetches a window of 32 anti-diagonals x 8 target columns below the
+	 * current cell (lane = diagonal), and every lane replays the same walk out of registers (one shuffle per
+	 * step) until it leaves the window: at least 8 and typically 16 steps per memory round trip.  A byte with
+	 * bit 7 set stands for upstream's force_state (cell outside the band of its diagonal). */
 	int n_cigar = 0;
-	if (lane == 0) {
-		int i0 = -1, j0 = -1;
+	{
+		int i = -1, j = -1;
 		const bool rev_cigar = (flag & EZ_REV_CIGAR) != 0;
-		if (!zdropped && !(flag & EZ_EXTZ_ONLY)) i0 = tlen - 1, j0 = qlen - 1;
-		else if (!zdropped && (flag & EZ_EXTZ_ONLY) && ez_mqe + end_bonus > ez_max) reach_end = 1, i0 = ez_mqe_t, j0 = qlen - 1;
-		else if (ez_max_t >= 0 && ez_max_q >= 0) i0 = ez_max_t, j0 = ez_max_q;
-		if (i0 >= 0 || j0 >= 0 || reach_end) {
-			int i = i0, j = j0, state = 0;
+		if (!zdropped && !(flag & EZ_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
+		else if (!zdropped && (flag & EZ_EXTZ_ONLY) && ez_mqe + end_bonus > ez_max) reach_end = 1, i = ez_mqe_t, j = qlen - 1;
+		else if (ez_max_t >= 0 && ez_max_q >= 0) i = ez_max_t, j = ez_max_q;
+		if (i >= 0 || j >= 0 || reach_end) {
+			int state = 0;
+			uint32_t cur_op = 0xf, cur_len = 0;      /* the open CIGAR run (all lanes agree; lane 0 writes) */
 			auto push = [&](uint32_t op, int len) {
-				if (n_cigar == 0 || op != (cigar[n_cigar - 1] & 0xf)) cigar[n_cigar++] = (uint32_t)len << 4 | op;
-				else cigar[n_cigar - 1] += (uint32_t)len << 4;
+				if (op != cur_op) {
+					if (cur_len) { if (lane == 0) cigar[n_cigar] = cur_len << 4 | cur_op; ++n_cigar; }
+					cur_op = op, cur_len = 0;
+				}
+				cur_len += (uint32_t)len;
 			};
 			while (i >= 0 && j >= 0) {
-				const int r = i + j;
-				int st = 0, en = tlen - 1, force_state = -1;
-				if (st < r - qlen + 1) st = r - qlen + 1;
-				if (en > r) en = r;
-				if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
-				if (en > (r + w) >> 1) en = (r + w) >> 1;
-				st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;  /* off[r], off_end[r] */
-				if (i < st) force_state = 2;
-				if (i > en) force_state = 1;
-				uint32_t tmp = force_state < 0 ? tb[(size_t)r * n_col + i - st] : 0;
-				if (state == 0) state = tmp & 7;
-				else if (!(tmp >> (state + 2) & 1)) state = 0;
-				if (state == 0) state = tmp & 7;
-				if (force_state >= 0) state = force_state;
-				if (state == 0) push(0, 1), --i, --j;
-				else if (state == 1 || state == 3) push(2, 1), --i;
-				else push(1, 1), --j;
+				const int r0 = i + j, i0 = i;
+				unsigned long long win = 0;
+				{
+					const int r = r0 - lane;
+					if (r >= 0) {
+						int st = 0, en = tlen - 1;
+						if (st < r - qlen + 1) st = r - qlen + 1;
+						if (en > r) en = r;
+						if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+						if (en > (r + w) >> 1) en = (r + w) >> 1;
+						st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;  /* off[r], off_end[r] */
+						const uint8_t *row = tb + (size_t)r * n_col - st;
+#pragma unroll
+						for (int k = 0; k < 8; ++k) {
+							const int ii = i0 - k;
+							unsigned long long v = 0;
+							if (ii >= 0) v = ii < st ? 0x82u : ii > en ? 0x81u : row[ii];
+							win |= v << (8 * k);
+						}
+					}
+				}
+				while (i >= 0 && j >= 0) {
+					const int dr = r0 - (i + j), di = i0 - i;
+					if (dr >= 32 || di >= 8) break;
+					const uint32_t tmp = (uint32_t)(__shfl_sync(MMG_FULL, win, dr) >> (8 * di)) & 0xff;
+					if (tmp & 0x80) state = (int)(tmp & 3);
+					else {
+						if (state == 0) state = tmp & 7;
+						else if (!(tmp >> (state + 2) & 1)) state = 0;
+						if (state == 0) state = tmp & 7;
+					}
+					if (state == 0) push(0, 1), --i, --j;
+					else if (state == 1 || state == 3) push(2, 1), --i;
+					else push(1, 1), --j;
+				}
 			}
 			if (i >= 0) push(2, i + 1);
 			if (j >= 0) push(1, j + 1);
+			push(0xf, 0);                              /* flush the open run */
+			__syncwarp();
 			if (!rev_cigar)
-				for (int k = 0; k < n_cigar >> 1; ++k) { uint32_t t = cigar[k]; cigar[k] = cigar[n_cigar - 1 - k], cigar[n_cigar - 1 - k] = t; }
+				for (int k = lane; k < n_cigar >> 1; k += 32) { uint32_t t = cigar[k]; cigar[k] = cigar[n_cigar - 1 - k], cigar[n_cigar - 1 - k] = t; }
 		}
+	}
+	if (lane == 0) {
 		res->max = ez_max, res->max_q = ez_max_q, res->max_t = ez_max_t, res->mqe = ez_mqe, res->mqe_t = ez_mqe_t, res->score = ez_score;
 		res->zdropped = (uint8_t)zdropped, res->reach_end = (uint8_t)reach_end, res->n_cigar = n_cigar;
 		*n_cell += cells;
@@ -951,7 +993,7 @@ __device__ int ext_inv_score(const DpMem &m, const DevOpt &o, int qlen, int pos[
 	return gmax > 32767 ? 32767 : gmax;
 }
 
-__global__ void __launch_bounds__(EXT_DP_WARPS * 32)
+__global__ void __launch_bounds__(EXT_DP_WARPS * 32, 4)
 ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint32_t j1, uint32_t *work)
 {
 	MMG_DYN_SMEM(smem_raw);
@@ -978,7 +1020,7 @@ ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint32
 			continue;
 		}
 		const int T16 = (tlen + 15) / 16 * 16, Q16 = (qlen + 15) / 16 * 16;
-		const size_t need = (size_t)8 * T16 + Q16 + 16 + (size_t)4 * T16;
+		const size_t need = EXT_DP_BYTES(T16, Q16);
 		DpMem m;
 		unsigned char *base = need <= EXT_SMEM_PER_WARP ? my_smem : xb.big + (size_t)(blockIdx.x * EXT_DP_WARPS + wib) * xb.big_per_warp;
 		if (need > EXT_SMEM_PER_WARP && need > xb.big_per_warp) { /* longer than the per-warp global slice: reported by the host */
