@@ -530,17 +530,17 @@ struct DpMem {
 };
 #define EXT_DP_BYTES(T16, Q16) ((size_t)18 * (T16) + (Q16) + 16)   /* H 4, ga/gb/gc 4 each, s 1, target 1 per column */
 
-/* scalar views of the packed arrays (boundary cells, the H bookkeeping) */
+/* scalar views of the packed arrays (boundary cells, the H bookkeeping): index of column t's 16-bit field */
 enum { DP_U, DP_Y, DP_X, DP_V, DP_X2, DP_Y2 };
-__device__ __forceinline__ uint16_t *dp_field(const DpMem &m, int a, int t)
+template<int A> __device__ __forceinline__ uint16_t *dp_field(const DpMem &m, int t)
 {
-	const int h = (t >> 1) & 1;
-	uint32_t *g = a == DP_U || a == DP_Y ? m.ga : a == DP_X || a == DP_V ? m.gb : m.gc;
-	const int word = a == DP_U || a == DP_X2 ? h : a == DP_Y || a == DP_Y2 ? 2 + h : a == DP_X ? 2 * h : 2 * h + 1;
-	return (uint16_t*)(g + (size_t)(t >> 2) * 4 + word) + (t & 1);
+	uint32_t *g = A == DP_U || A == DP_Y ? m.ga : A == DP_X || A == DP_V ? m.gb : m.gc;
+	const int lo = A == DP_X || A == DP_V ? (t & 2) * 2 + (t & 1) : (t & 3);     /* gb interleaves x and v per pair */
+	const int off = A == DP_Y || A == DP_Y2 ? 4 : A == DP_V ? 2 : 0;
+	return (uint16_t*)g + 2 * (t & ~3) + lo + off;
 }
-__device__ __forceinline__ int dp_get(const DpMem &m, int a, int t) { return (int)*dp_field(m, a, t) - 128; }
-__device__ __forceinline__ void dp_set(const DpMem &m, int a, int t, int v) { *dp_field(m, a, t) = (uint16_t)(v + 128); }
+template<int A> __device__ __forceinline__ int dp_get(const DpMem &m, int t) { return (int)*dp_field<A>(m, t) - 128; }
+template<int A> __device__ __forceinline__ void dp_set(const DpMem &m, int t, int v) { *dp_field<A>(m, t) = (uint16_t)(v + 128); }
 
 __device__ __forceinline__ bool ez_apply_zdrop(int32_t *ez_max, int *ez_max_t, int *ez_max_q, int32_t H, int r, int t, int zdrop, int e)
 { /* ksw2.h ksw_apply_zdrop with is_rot = 1 */
@@ -701,10 +701,12 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 		st0 = st, en0 = en;
 		st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;
 		const int bnd = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
-		int x1 = -q - e, x21 = -q2 - e2, v1 = st > 0 ? -q - e : bnd;
-		if (st > 0 && st - 1 >= last_st && st - 1 <= last_en) x1 = dp_get(m, DP_X, st - 1), x21 = dp_get(m, DP_X2, st - 1), v1 = dp_get(m, DP_V, st - 1);
+		/* the left neighbour of column st: upstream takes x[st-1], v[st-1], x2[st-1] only when that column was
+		 * computed on the previous diagonal (the sweep reads them with everything else), else the boundary values */
+		const bool edge_mem = st > 0 && st - 1 >= last_st && st - 1 <= last_en;
+		const uint32_t x1 = (uint32_t)(128 - q - e) << 16, x21 = (uint32_t)(128 - q2 - e2) << 16, v1 = (uint32_t)(128 + (st > 0 ? -q - e : bnd)) << 16;
 		__syncwarp();
-		if (en >= r && lane < 3) dp_set(m, lane == 0 ? DP_Y : lane == 1 ? DP_Y2 : DP_U, r, lane == 0 ? -q - e : lane == 1 ? -q2 - e2 : bnd);
+		if (en >= r && lane == 0) dp_set<DP_Y>(m, r, -q - e), dp_set<DP_Y2>(m, r, -q2 - e2), dp_set<DP_U>(m, r, bnd);
 		__syncwarp();
 		/* One sweep per 128 columns (four per lane, as two 16x2 words), from high t to low t.
 		 * Scores: upstream stores 16 lanes at a time starting at st0 (lanes past en0 included; bytes below st0 keep
@@ -739,7 +741,7 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 			if (act) {
 				const DpQuad a = *(const DpQuad*)(m.ga + t), b = *(const DpQuad*)(m.gb + t), c = *(const DpQuad*)(m.gc + t);
 				A0 = a.x, A1 = a.y, A2 = a.z, A3 = a.w, B0 = b.x, B1 = b.y, B2 = b.z, B3 = b.w, C0 = c.x, C1 = c.y, C2 = c.z, C3 = c.w;
-				if (t == st) xp = (uint32_t)(x1 + 128) << 16, vp = (uint32_t)(v1 + 128) << 16, x2p = (uint32_t)(x21 + 128) << 16;
+				if (t == st && !edge_mem) xp = x1, vp = v1, x2p = x21;
 				else {
 					const DpPair pb = *(const DpPair*)(m.gb + t - 2);
 					xp = pb.x, vp = pb.y, x2p = m.gc[t - 3];
@@ -764,12 +766,12 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 			int32_t max_H, max_t;
 			if (r > 0) {
 				const int en1 = st0 + (en0 - st0) / 4 * 4;
-				int32_t hen = en0 > 0 ? m.H[en0 - 1] + dp_get(m, DP_U, en0) : m.H[en0] + dp_get(m, DP_V, en0);
+				int32_t hen = en0 > 0 ? m.H[en0 - 1] + dp_get<DP_U>(m, en0) : m.H[en0] + dp_get<DP_V>(m, en0);
 				__syncwarp();
 				/* H[t] += v[t] for t in [st0, en0); upstream's 4-lane SSE max followed by a scalar tail */
 				long long kg = -1, kr = -1; /* (value, tie) keys; larger wins */
 				for (int t = st0 + lane; t < en0; t += 32) {
-					int32_t h = m.H[t] + dp_get(m, DP_V, t);
+					int32_t h = m.H[t] + dp_get<DP_V>(m, t);
 					m.H[t] = h;
 					if (t < en1) { /* group region: value, then SSE lane (t-st0)&3 ascending, then t ascending */
 						long long k = ((long long)h - KSW_NEG_INF) << 28 | (long long)(3 - ((t - st0) & 3)) << 26 | (long long)(0x3ffffff - t);
@@ -797,7 +799,7 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 				}
 				__syncwarp();
 			} else {
-				max_H = dp_get(m, DP_V, 0) - qe, max_t = 0;
+				max_H = dp_get<DP_V>(m, 0) - qe, max_t = 0;
 				__syncwarp();
 				if (lane == 0) m.H[0] = max_H;
 				__syncwarp();
@@ -810,15 +812,15 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 		} else {
 			if (r > 0) {
 				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
-					int32_t d0 = dp_get(m, DP_V, last_H0_t), d1 = dp_get(m, DP_U, last_H0_t + 1);
+					int32_t d0 = dp_get<DP_V>(m, last_H0_t), d1 = dp_get<DP_U>(m, last_H0_t + 1);
 					if (d0 > d1) H0 += d0;
 					else H0 += d1, ++last_H0_t;
 				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
-					H0 += dp_get(m, DP_V, last_H0_t);
+					H0 += dp_get<DP_V>(m, last_H0_t);
 				} else {
-					++last_H0_t, H0 += dp_get(m, DP_U, last_H0_t);
+					++last_H0_t, H0 += dp_get<DP_U>(m, last_H0_t);
 				}
-			} else H0 = dp_get(m, DP_V, 0) - qe, last_H0_t = 0;
+			} else H0 = dp_get<DP_V>(m, 0) - qe, last_H0_t = 0;
 			if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H0;
 		}
 		last_st = st, last_en = en;
