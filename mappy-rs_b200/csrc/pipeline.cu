@@ -138,6 +138,7 @@ struct mmg_batch {
 	bool uploaded, ran, fetched;
 	bool streamed;                     /* inputs/results go through the aligner's streaming slots */
 	HostPool *pool; mmg_hit_t *ph; uint64_t ph_bytes; /* streamed: the hit records live in a pinned pool block */
+	uint32_t *pc; uint64_t pc_bytes;                  /* streamed, CIGAR mode: so do the CIGAR operations */
 	/* debug: arenas of the LAST chunk stay valid until the next run */
 	uint32_t dbg_r0, dbg_r1;
 };
@@ -421,7 +422,7 @@ int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets
 	b->d_bases = 0, b->d_off = 0, b->d_hits = 0, b->d_nregs = 0, b->d_stats = 0, b->d_cigar = 0, b->cigar_cap = 0, b->n_cigar_dev = 0;
 	b->uploaded = b->ran = b->fetched = false;
 	b->streamed = false;
-	b->pool = 0, b->ph = 0, b->ph_bytes = 0;
+	b->pool = 0, b->ph = 0, b->ph_bytes = 0, b->pc = 0, b->pc_bytes = 0;
 	memset(b->stats, 0, sizeof(b->stats));
 	for (uint32_t i = 0; i < n_reads; ++i) {
 		uint64_t l = offsets[i + 1] - offsets[i];
@@ -599,8 +600,6 @@ static int slot_drain(mmg_aligner *al, mmg_batch *b, int k)
 	mmg_aligner::ResSlot &r = al->rs[k];
 	if (!r.pending) return MMG_OK;
 	CK(cudaEventSynchronize(r.ev_out));
-	if (b->cigar.size() < r.cigar_base + r.n_cigar) b->cigar.resize(r.cigar_base + r.n_cigar);
-	if (r.n_cigar) memcpy(b->cigar.data() + r.cigar_base, r.h_cigar, r.n_cigar * 4);
 	uint64_t acc = r.hit_base;
 	for (uint32_t i = 0; i < r.n_reads; ++i) b->hit_off[r.read0 + i] = acc, acc += r.h_nregs[i];
 	if (acc != r.hit_base + r.n_hits) { mmg_set_error("internal: hit count mismatch in a result slot (%llu vs %llu)", (unsigned long long)acc, (unsigned long long)(r.hit_base + r.n_hits)); return MMG_ECUDA; }
@@ -736,6 +735,14 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 				pool_release(b->pool, b->ph, b->ph_bytes);
 				b->ph = np, b->ph_bytes = nb;
 			}
+			if (with_cigar && (b->n_cigar_dev + n_cg_sub) * 4 > b->pc_bytes) { /* rare: more operations than reserved */
+				uint64_t nb = 0;
+				uint32_t *np = (uint32_t*)pool_acquire(b->pool, 2 * (b->n_cigar_dev + n_cg_sub) * 4, &nb);
+				if (!np) { mmg_set_error("cannot allocate pinned memory for the results"); return MMG_ENOMEM; }
+				CK(cudaStreamSynchronize(al->s_out));
+				if (b->pc) { memcpy(np, b->pc, b->n_cigar_dev * 4); pool_release(b->pool, b->pc, b->pc_bytes); }
+				b->pc = np, b->pc_bytes = nb;
+			}
 			if ((rc = slot_grow(&r.d_nregs, &r.h_nregs, &r.nregs_cap, (uint64_t)(s1 - s0) + 1))) return rc;
 			if (with_cigar && (rc = slot_grow(&r.d_cigar, &r.h_cigar, &r.cigar_cap, n_cg_sub + 1))) return rc;
 			STAGE_BEGIN();
@@ -746,7 +753,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 			CK(cudaEventRecord(r.ev_packed, st));
 			CK(cudaStreamWaitEvent(al->s_out, r.ev_packed, 0));
 			if (n_hits_sub) CK(cudaMemcpyAsync(b->ph + b->n_hits_dev, r.d_hits, n_hits_sub * sizeof(mmg_hit_t), cudaMemcpyDeviceToHost, al->s_out));
-			if (n_cg_sub) CK(cudaMemcpyAsync(r.h_cigar, r.d_cigar, n_cg_sub * 4, cudaMemcpyDeviceToHost, al->s_out));
+			if (n_cg_sub) CK(cudaMemcpyAsync(b->pc + b->n_cigar_dev, r.d_cigar, n_cg_sub * 4, cudaMemcpyDeviceToHost, al->s_out));
 			CK(cudaMemcpyAsync(r.h_nregs, r.d_nregs, (size_t)(s1 - s0) * 4, cudaMemcpyDeviceToHost, al->s_out));
 			CK(cudaEventRecord(r.ev_out, al->s_out));
 			/* the next sub-range that packs into this slot must not start before the copy-out is done */
@@ -860,6 +867,10 @@ static int map_batch_streamed(mmg_aligner *al, mmg_batch *b)
 	b->pool = al->pool;
 	b->ph = (mmg_hit_t*)pool_acquire(b->pool, ((uint64_t)b->n_reads + (b->n_reads >> 3) + 1024) * sizeof(mmg_hit_t), &b->ph_bytes);
 	if (!b->ph) { b->pool = 0; mmg_set_error("cannot allocate pinned memory for the results"); return MMG_ENOMEM; }
+	if (al->mo.flag & MMG_F_CIGAR) { /* ~0.09 operations per base on 8 %-error reads; grown on demand */
+		b->pc = (uint32_t*)pool_acquire(b->pool, (b->n_bases / 8 + 65536) * 4, &b->pc_bytes);
+		if (!b->pc) { mmg_set_error("cannot allocate pinned memory for the results"); return MMG_ENOMEM; }
+	}
 	std::vector<uint32_t> cuts;
 	cut_chunks(al, b, cuts, true);
 	const size_t n_chunks = cuts.size() - 1;
@@ -901,7 +912,6 @@ static int map_batch_streamed(mmg_aligner *al, mmg_batch *b)
 	CK(cudaGetLastError());
 	{ float ms = 0; cudaEventElapsedTime(&ms, al->ev_run0, al->ev_run1); al->last_run_ms = ms; }
 	stage_collect(al);
-	b->cigar.resize(b->n_cigar_dev);
 	b->hit_off[b->n_reads] = b->n_hits_dev;
 	b->ran = b->fetched = true;
 	return MMG_OK;
@@ -924,7 +934,7 @@ int mmg_map_batch(mmg_aligner *al, const char *bases, const uint64_t *offsets, u
 	b->hits_cap = 0, b->n_hits_dev = 0;
 	b->uploaded = b->ran = b->fetched = false;
 	b->streamed = true;
-	b->pool = 0, b->ph = 0, b->ph_bytes = 0;
+	b->pool = 0, b->ph = 0, b->ph_bytes = 0, b->pc = 0, b->pc_bytes = 0;
 	b->dbg_r0 = b->dbg_r1 = 0;
 	memset(b->stats, 0, sizeof(b->stats));
 	int rc = map_batch_streamed(al, b);
@@ -941,6 +951,7 @@ void mmg_batch_destroy(mmg_batch *b)
 {
 	if (!b) return;
 	if (b->ph && b->pool) pool_release(b->pool, b->ph, b->ph_bytes);
+	if (b->pc && b->pool) pool_release(b->pool, b->pc, b->pc_bytes);
 	if (b->d_bases) cudaFree(b->d_bases);
 	if (b->d_off) cudaFree(b->d_off);
 	if (b->d_hits) cudaFree(b->d_hits);
@@ -954,8 +965,8 @@ uint32_t mmg_batch_n_reads(const mmg_batch *b) { return b->n_reads; }
 uint64_t mmg_batch_n_hits(const mmg_batch *b) { return b->streamed ? b->n_hits_dev : b->hits.size(); }
 const uint64_t *mmg_batch_hit_off(const mmg_batch *b) { return b->hit_off.data(); }
 const mmg_hit_t *mmg_batch_hits(const mmg_batch *b) { return b->streamed ? b->ph : b->hits.data(); }
-uint64_t mmg_batch_n_cigar(const mmg_batch *b) { return b->cigar.size(); }
-const uint32_t *mmg_batch_cigar(const mmg_batch *b) { return b->cigar.data(); }
+uint64_t mmg_batch_n_cigar(const mmg_batch *b) { return b->streamed ? b->n_cigar_dev : b->cigar.size(); }
+const uint32_t *mmg_batch_cigar(const mmg_batch *b) { return b->streamed ? b->pc : b->cigar.data(); }
 int mmg_batch_stats(const mmg_batch *b, uint64_t out[MMG_N_STATS]) { memcpy(out, b->stats, sizeof(b->stats)); return MMG_OK; }
 
 int mmg_stage_times(const mmg_aligner *al, double ms[MMG_N_STAGES], uint64_t launches[MMG_N_STAGES])
