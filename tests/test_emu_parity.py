@@ -156,6 +156,22 @@ def test_cigar_mode_splits_and_inversions(emu_lib, oracle_mod):
         c.close()
 
 
+def test_cigar_mode_hifi_scoring(emu_lib, oracle_mod):
+    """map-hifi (k=19, w=19; a=1 b=4 q=6 e=2 q2=26 e2=1): the packed two-cells-per-register DP under the second
+    scoring set, left- and right-aligned extensions and gap fills, bit-exact CIGARs."""
+    ref, coff, names, seqs = parity.random_reference(23, [120000])
+    c = parity.Case(emu_lib, names, seqs, preset="map-hifi", cigar=True)
+    try:
+        _small_arenas(c)
+        buf, offs, _ = data_gen.make_reads(24, ref, coff, 24, 1500, 4000, p_sub=0.004, p_ins=0.003, p_del=0.003)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_hits(dev, ora) == []
+        assert len(dev.cigar) == len(ora.cigar) > 100
+    finally:
+        c.close()
+
+
 def test_cigar_mode_fixture_map_one(emu_lib, oracle_mod):
     """`map_one` through the product's kernel source: 1 hit, 0..400, 400M (src/lib.rs:1094-1106)."""
     c = parity.Case(emu_lib, None, None, mmi=MMI, cigar=True)
