@@ -774,19 +774,33 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 static void cut_chunks(const mmg_aligner *al, const mmg_batch *b, std::vector<uint32_t> &cuts, bool ramp)
 {
 	const uint32_t n = b->n_reads;
-	cuts.clear();
-	cuts.push_back(0);
-	int shift = ramp ? al->ramp_shift : 0;
-	for (uint32_t r0 = 0; r0 < n;) {
-		uint32_t r1 = r0;
-		const uint64_t cap = al->cap_bases >> shift;
-		while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= cap) ++r1;
-		if (r1 == r0) { /* a read longer than the ramped size (reads longer than the arena were rejected earlier) */
-			while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= al->cap_bases) ++r1;
+	if (al->mo.flag & MMG_F_CIGAR) ramp = false; /* extension dominates and scales with the bases: equal chunks, the copy-in is negligible */
+	/* pass 0 fills every chunk to the arena (that fixes the number of chunks); pass 1 cuts the same number of chunks
+	 * evenly, so that the last one is not a sliver that pays a full set of kernel tails for little work */
+	size_t n_greedy = 0;
+	for (int pass = 0; pass < 2; ++pass) {
+		cuts.clear();
+		cuts.push_back(0);
+		int shift = ramp ? al->ramp_shift : 0;
+		size_t k = 0;
+		for (uint32_t r0 = 0; r0 < n; ++k) {
+			uint32_t r1 = r0;
+			uint64_t cap = al->cap_bases >> shift;
+			if (pass == 1 && n_greedy > 1 && k < n_greedy) { /* even share of what is left, the ramped first chunk counting for its fraction */
+				const double w = shift ? 1.0 / (double)(1 << shift) : 1.0, left_w = w + (double)(n_greedy - 1 - k);
+				const uint64_t share = (uint64_t)((double)(b->off[n] - b->off[r0]) * w / left_w) + 1;
+				if (share < cap) cap = share;
+			}
+			while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= cap) ++r1;
+			if (r1 == r0) { /* a read longer than the ramped / even size (reads longer than the arena were rejected earlier) */
+				while (r1 < n && r1 - r0 < al->cap_reads && b->off[r1 + 1] - b->off[r0] <= al->cap_bases) ++r1;
+				if (r1 > r0 + 1 && pass == 1) r1 = r0 + 1;
+			}
+			cuts.push_back(r1);
+			r0 = r1;
+			shift = 0; /* one small first chunk, then full chunks */
 		}
-		cuts.push_back(r1);
-		r0 = r1;
-		shift = 0; /* one small first chunk, then full chunks */
+		if (pass == 0) { n_greedy = cuts.size() - 1; if (n_greedy <= 1) break; }
 	}
 }
 
