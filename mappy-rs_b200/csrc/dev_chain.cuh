@@ -71,15 +71,20 @@ static __device__ void dev_backtrack_compact(int n, uint64_t *ax, uint64_t *ay, 
 				int best_len = 0;
 				int32_t max_s = 0;
 				if (lane == 0) {
-					int m = 0, cur = czi;
-					do {
+					/* the walk is a chain of dependent loads: f, t and p of the next anchor are fetched together,
+					 * one round trip per step */
+					int m = 0, cur = czi, nxt = p[cur];
+					for (;;) {
 						v[n_v + m] = cur, ++m;
-						const int nxt = p[cur];
-						const int32_t sc1 = nxt < 0 ? czkx : czkx - f[nxt];
+						int32_t fn = 0, tn = 0, pn = -1;
+						if (nxt >= 0) fn = f[nxt], tn = t[nxt], pn = p[nxt];
+						const int32_t sc1 = nxt < 0 ? czkx : czkx - fn;
 						cur = nxt;
 						if (sc1 > max_s) max_s = sc1, best_len = m;
 						else if (max_s - sc1 > max_drop) break;
-					} while (cur >= 0 && t[cur] == 0);
+						if (cur < 0 || tn != 0) break;
+						nxt = pn;
+					}
 				}
 				best_len = __shfl_sync(MMG_FULL, best_len, 0);
 				max_s = __shfl_sync(MMG_FULL, max_s, 0);
