@@ -172,6 +172,42 @@ def test_cigar_mode_hifi_scoring(emu_lib, oracle_mod):
         c.close()
 
 
+def test_cigar_mode_ambiguous_bases_and_long_gaps(emu_lib, oracle_mod):
+    """N bases in reads and reference (the sc_ambi score and the n_ambi counts of mm_update_extra) and reads with
+    30-120 base insertions / deletions (the long-gap x2/y2 states of ksw_extd2): CIGAR, NM, dp_max, mapq bit-exact."""
+    import numpy as np
+    rng = np.random.default_rng(77)
+    ref, coff, names, seqs = parity.random_reference(63, [150000])
+    refb = bytearray(seqs[0].encode() if isinstance(seqs[0], str) else seqs[0])
+    for p0 in rng.integers(1000, len(refb) - 1000, 40):
+        refb[p0:p0 + int(rng.integers(1, 6))] = b"N" * 5
+    seqs = [bytes(refb[:len(seqs[0])]).decode()]
+    c = parity.Case(emu_lib, names, seqs, cigar=True)
+    try:
+        _small_arenas(c)
+        buf, offs, _ = data_gen.make_reads(78, ref, coff, 60, 800, 3000)
+        buf = np.array(np.frombuffer(bytes(buf), dtype=np.uint8))
+        offs = np.asarray(offs)
+        buf[rng.integers(0, len(buf), len(buf) // 150)] = ord("N")
+        pieces = []
+        for i in range(len(offs) - 1):                     # a long deletion or insertion in every other read
+            r = buf[offs[i]:offs[i + 1]]
+            if i % 2 == 0 and len(r) > 600:
+                cut = int(rng.integers(200, len(r) - 300)); g = int(rng.integers(30, 120))
+                r = np.concatenate([r[:cut], r[cut + g:]]) if i % 4 == 0 else np.concatenate([r[:cut], rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), g), r[cut:]])
+            pieces.append(r)
+        offs2 = np.zeros(len(pieces) + 1, dtype=np.uint64)
+        offs2[1:] = np.cumsum([len(x) for x in pieces])
+        buf2 = np.concatenate(pieces)
+        dev = c.aligner.map_batch(buf2, offs2)
+        ora = c.oracle.map_batch(buf2, offs2, 4)
+        assert parity.compare_hits(dev, ora) == []
+        assert len(dev.cigar) == len(ora.cigar) > 500
+        assert any(((int(x) & 15) in (1, 2)) and (int(x) >> 4) >= 30 for x in ora.cigar)   # long gaps really occur
+    finally:
+        c.close()
+
+
 def test_cigar_mode_fixture_map_one(emu_lib, oracle_mod):
     """`map_one` through the product's kernel source: 1 hit, 0..400, 400M (src/lib.rs:1094-1106)."""
     c = parity.Case(emu_lib, None, None, mmi=MMI, cigar=True)
