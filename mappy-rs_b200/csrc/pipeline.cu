@@ -577,15 +577,17 @@ static int stream_setup(mmg_aligner *al)
 	return MMG_OK;
 }
 
+/* h = 0: device staging only (hits and CIGARs are copied out straight into the batch's pinned pool block) */
 template<typename T> static int slot_grow(T **d, T **h, uint64_t *cap, uint64_t need)
 {
 	if (need <= *cap) return MMG_OK;
 	uint64_t n = *cap ? *cap : 1024;
 	while (n < need) n *= 2;
 	if (*d) cudaFree(*d);
-	if (*h) cudaFreeHost(*h);
-	*d = 0, *h = 0, *cap = 0;
-	if (cudaMalloc((void**)d, n * sizeof(T)) != cudaSuccess || cudaMallocHost((void**)h, n * sizeof(T)) != cudaSuccess) {
+	if (h && *h) cudaFreeHost(*h);
+	*d = 0, *cap = 0;
+	if (h) *h = 0;
+	if (cudaMalloc((void**)d, n * sizeof(T)) != cudaSuccess || (h && cudaMallocHost((void**)h, n * sizeof(T)) != cudaSuccess)) {
 		mmg_set_error("cannot allocate %llu bytes for a result slot", (unsigned long long)(n * sizeof(T)));
 		return MMG_ENOMEM;
 	}
@@ -725,7 +727,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 			mmg_aligner::ResSlot &r = al->rs[k];
 			int rc;
 			if ((rc = slot_drain(al, b, k))) return rc;
-			if ((rc = slot_grow(&r.d_hits, &r.h_hits, &r.hits_cap, n_hits_sub + 1))) return rc;
+			if ((rc = slot_grow(&r.d_hits, (mmg_hit_t**)0, &r.hits_cap, n_hits_sub + 1))) return rc;
 			if ((b->n_hits_dev + n_hits_sub) * sizeof(mmg_hit_t) > b->ph_bytes) { /* rare: more hits than reserved */
 				uint64_t nb = 0;
 				mmg_hit_t *np = (mmg_hit_t*)pool_acquire(b->pool, 2 * (b->n_hits_dev + n_hits_sub) * sizeof(mmg_hit_t), &nb);
@@ -744,7 +746,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 				b->pc = np, b->pc_bytes = nb;
 			}
 			if ((rc = slot_grow(&r.d_nregs, &r.h_nregs, &r.nregs_cap, (uint64_t)(s1 - s0) + 1))) return rc;
-			if (with_cigar && (rc = slot_grow(&r.d_cigar, &r.h_cigar, &r.cigar_cap, n_cg_sub + 1))) return rc;
+			if (with_cigar && (rc = slot_grow(&r.d_cigar, (uint32_t**)0, &r.cigar_cap, n_cg_sub + 1))) return rc;
 			STAGE_BEGIN();
 			launch_pack_hits(c, s0, s1, r.d_hits, al->n_sms, st);
 			if (with_cigar) launch_pack_cigar(c, al->xb, s0, s1, r.d_hits, r.d_cigar, b->n_cigar_dev, al->cg_read_off, al->n_sms, st);
