@@ -195,12 +195,17 @@ chain_dp_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, uint32_t *work)
 					if (over) brk = __ffs((int)over) - 1;
 					else n_skip = __shfl_sync(MMG_FULL, after, 31);
 				}
-				const int limit = brk >= 0 ? brk : 32;
-				const int32_t c2 = lane < limit ? sc : INT32_MIN_;
-				const int32_t mx = __reduce_max_sync(MMG_FULL, c2);
+				/* best score among the lanes before the break; without a break that is the step's maximum from above */
+				int32_t mx = mxs;
+				uint32_t at_mx = top;
+				if (brk >= 0) {
+					const int32_t c2 = lane < brk ? sc : INT32_MIN_;
+					mx = __reduce_max_sync(MMG_FULL, c2);
+					at_mx = __ballot_sync(MMG_FULL, c2 == mx);
+				}
 				if (mx > max_f) {
 					max_f = mx;
-					max_j = jb - (__ffs((int)__ballot_sync(MMG_FULL, c2 == mx)) - 1);
+					max_j = jb - (__ffs((int)at_mx) - 1);
 				}
 				if (brk >= 0) end_j = jb - brk, broke = true;
 			}
