@@ -640,10 +640,9 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
                                            uint8_t *tb, uint32_t *cigar, ExtJob *res, unsigned long long *n_cell)
 {
 	DpMem m;
-	if (SMEM) {
-		MMG_DYN_SMEM(dp_smem);
-		ext_dpmem_set(m, dp_smem + (size_t)(threadIdx.x >> 5) * EXT_SMEM_PER_WARP, T16, Q16);
-	} else ext_dpmem_set(m, gbase, T16, Q16);
+	MMG_DYN_SMEM(dp_smem);
+	if (SMEM) ext_dpmem_set(m, dp_smem + (size_t)(threadIdx.x >> 5) * EXT_SMEM_PER_WARP, T16, Q16);
+	else ext_dpmem_set(m, gbase, T16, Q16);
 	const int lane = mmg_lane();
 	int q = o.q, e = o.e, q2 = o.q2, e2 = o.e2;
 	if (q2 + e2 < q + e) { int t = q; q = q2, q2 = t, t = e, e = e2, e2 = t; }
@@ -660,8 +659,10 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 	const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
 	/* constants of the packed core (dp_cell2): every term is carried with bias 256, its test constant puts
 	 * "term - z + gap_open > 0" (left-aligned; ">= 0" right-aligned) into bit 12, 13, 14 or 15 of its field */
-	DpK dk;
-	{
+	/* (kept in the warp's slot of shared memory behind the DP slices: the pass has no registers to spare) */
+	DpK &dk = *(DpK*)(dp_smem + (size_t)EXT_DP_WARPS * EXT_SMEM_PER_WARP + (size_t)(threadIdx.x >> 5) * EXT_DPK_BYTES);
+	__syncwarp();
+	if (lane == 0) {
 		const int ge = right ? 0 : 1;
 		dk.right = right;
 		dk.p_s = DP_W(128 * 8 + (right ? 0 : 4)), dk.p_a = DP_W(right ? 1 : 3), dk.p_b = DP_W(2), dk.p_a2 = DP_W(right ? 3 : 1), dk.p_b2 = DP_W(right ? 4 : 0);
@@ -671,6 +672,7 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 		dk.ra2 = DP_W((uint16_t)(128 - qe2 - (16384 - ge))), dk.rb2 = DP_W((uint16_t)(128 - qe2 - (32768 - ge)));
 		dk.floor1 = DP_W((uint16_t)(128 - qe)), dk.floor2 = DP_W((uint16_t)(128 - qe2));
 	}
+	__syncwarp();
 	const uint32_t sc_b4 = (uint32_t)(sc_mch + 128) * 0x01010101u, scN_b4 = (uint32_t)(sc_N + 128) * 0x01010101u;
 	/* ksw_reset_extz */
 	int32_t ez_max = 0, ez_score = KSW_NEG_INF, ez_mqe = KSW_NEG_INF, ez_mte = KSW_NEG_INF;

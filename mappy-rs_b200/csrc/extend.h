@@ -5,6 +5,7 @@
 
 #define EXT_DP_WARPS 4
 #define EXT_SMEM_PER_WARP 12288   /* bytes of shared memory per DP warp (18 B per target column + the query): jobs up to ~640 x 640 bases, longer ones use the global slice */
+#define EXT_DPK_BYTES 96         /* per-warp slot of the pass constants (struct DpK) behind the DP slices */
 #define EXT_LEFT 0
 #define EXT_FILL 1
 #define EXT_RIGHT 2
