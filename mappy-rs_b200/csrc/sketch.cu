@@ -201,8 +201,7 @@ sketch_kernel(ChunkDev c, int w, int k, uint32_t *work)
 				 * earlier steps left theirs there).  log2(w) combines instead of w. */
 				KT cv = xe;
 				uint32_t cm = 1u << 8; /* age 0, one copy */
-				int K = 0;
-				while ((2 << K) <= w) ++K;
+				const int K = 31 - __clz(w);     /* floor(log2(w)) */
 				for (int q = 1; q <= K; ++q) {
 					const int half = 1 << (q - 1);
 					KT *lv = lvl_v + (size_t)(q > 1 ? q - 2 : 0) * RING;   /* ring of level q-1 (levels >= 1 sit at index level-1) */
