@@ -73,36 +73,62 @@ __device__ __forceinline__ void heap_down(uint64_t *l, int i, int n)
 	l[i] = tmp;
 }
 
-/* seed.c: mm_seed_select, run by one lane (only reads with a high-occurrence seed get here) */
-__device__ void dev_seed_select(int n, const uint32_t *sn, const uint32_t *sq, uint32_t *meta, int len, int max_occ, int max_max_occ, int dist, uint64_t *b)
+/* seed.c: mm_seed_select.  A streak is a maximal run [st, en) of seeds that occur more than max_occ times; upstream
+ * keeps the (pe - ps) / dist least frequent of each streak (a heap) and drops the rest.  The streaks are found by the
+ * warp (ballots over 32 seeds at a time); the heap of a streak runs on lane 0 - streaks are short and rare. */
+__device__ void dev_seed_streak(int st, int en, int n, const uint32_t *sn, const uint32_t *sq, uint32_t *meta, int len, int max_max_occ, int dist, uint64_t *b)
 {
-	if (n == 0 || n == 1) return;
-	for (int i = 0, last0 = -1; i <= n; ++i) {
-		if (i == n || (int)sn[i] <= max_occ) {
-			if (i - last0 > 1) {
-				int ps = last0 < 0 ? 0 : (int)(sq[last0] >> 1);
-				int pe = i == n ? len : (int)(sq[i] >> 1);
-				int j, k, st = last0 + 1, en = i;
-				int max_high_occ = (int)((double)(pe - ps) / dist + .499);
-				if (max_high_occ > 0) {
-					if (max_high_occ > MAX_MAX_HIGH_OCC) max_high_occ = MAX_MAX_HIGH_OCC;
-					for (j = st, k = 0; j < en && k < max_high_occ; ++j, ++k)
-						b[k] = (uint64_t)sn[j] << 32 | (uint32_t)j;
-					for (int h = (k >> 1) - 1; h >= 0; --h) heap_down(b, h, k);
-					for (; j < en; ++j) {
-						if (sn[j] < (uint32_t)(b[0] >> 32)) {
-							b[0] = (uint64_t)sn[j] << 32 | (uint32_t)j;
-							heap_down(b, 0, k);
-						}
-					}
-					for (j = 0; j < k; ++j) meta[(uint32_t)b[j]] |= 2u;
-				}
-				for (j = st; j < en; ++j) meta[j] ^= 2u;
-				for (j = st; j < en; ++j)
-					if ((int)sn[j] > max_max_occ) meta[j] |= 2u;
+	int ps = st == 0 ? 0 : (int)(sq[st - 1] >> 1);
+	int pe = en == n ? len : (int)(sq[en] >> 1);
+	int j, k;
+	int max_high_occ = (int)((double)(pe - ps) / dist + .499);
+	if (max_high_occ > 0) {
+		if (max_high_occ > MAX_MAX_HIGH_OCC) max_high_occ = MAX_MAX_HIGH_OCC;
+		for (j = st, k = 0; j < en && k < max_high_occ; ++j, ++k)
+			b[k] = (uint64_t)sn[j] << 32 | (uint32_t)j;
+		for (int h = (k >> 1) - 1; h >= 0; --h) heap_down(b, h, k);
+		for (; j < en; ++j) {
+			if (sn[j] < (uint32_t)(b[0] >> 32)) {
+				b[0] = (uint64_t)sn[j] << 32 | (uint32_t)j;
+				heap_down(b, 0, k);
 			}
-			last0 = i;
 		}
+		for (j = 0; j < k; ++j) meta[(uint32_t)b[j]] |= 2u;
+	}
+	for (j = st; j < en; ++j) meta[j] ^= 2u;
+	for (j = st; j < en; ++j)
+		if ((int)sn[j] > max_max_occ) meta[j] |= 2u;
+}
+
+__device__ void dev_seed_select(int n, const uint32_t *sn, const uint32_t *sq, uint32_t *meta, int len, int max_occ, int max_max_occ, int dist, uint64_t *b)
+{ /* all lanes */
+	if (n == 0 || n == 1) return;
+	const int lane = mmg_lane();
+	int run_st = -1;
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + lane;
+		const uint32_t hm = __ballot_sync(MMG_FULL, i < n && (int)sn[i] > max_occ);
+		int p = 0; /* bits below p are done */
+		while (p < 32) {
+			const uint32_t up = ~0u << p;
+			if (run_st < 0) {
+				const uint32_t mm = hm & up;
+				if (!mm) break;
+				const int bpos = __ffs((int)mm) - 1;
+				run_st = i0 + bpos, p = bpos + 1;
+			} else {
+				const uint32_t zz = ~hm & up;
+				if (!zz) break; /* the streak runs into the next 32 seeds */
+				const int bpos = __ffs((int)zz) - 1;
+				if (lane == 0) dev_seed_streak(run_st, i0 + bpos, n, sn, sq, meta, len, max_max_occ, dist, b);
+				__syncwarp();
+				run_st = -1, p = bpos + 1;
+			}
+		}
+	}
+	if (run_st >= 0) { /* only when n is a multiple of 32 and the last seed is in a streak */
+		if (lane == 0) dev_seed_streak(run_st, n, n, sn, sq, meta, len, max_max_occ, dist, b);
+		__syncwarp();
 	}
 }
 
@@ -218,7 +244,7 @@ seed_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 		/* ---- mm_seed_select / plain occurrence cut ---- */
 		if (n_high > 0) {
 			if (o.occ_dist > 0 && o.max_max_occ > o.mid_occ) {
-				if (lane == 0) dev_seed_select(n_m0, sn, sq, sm, qlen, o.mid_occ, o.max_max_occ, o.occ_dist, s_heap[wib]);
+				dev_seed_select(n_m0, sn, sq, sm, qlen, o.mid_occ, o.max_max_occ, o.occ_dist, s_heap[wib]);
 			} else {
 				for (int i = lane; i < n_m0; i += 32) if ((int)sn[i] > o.mid_occ) sm[i] |= 2u;
 			}
@@ -229,25 +255,35 @@ seed_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t *work)
 		int n_m = n_m0, rep_len = 0;
 		unsigned long long n_a = 0;
 		if (n_high > 0) {
-			if (lane == 0) { /* serial: the interval union depends on order */
-				int rep_st = 0, rep_en = 0, k = 0;
-				for (int i = 0; i < n_m0; ++i) {
-					if (sm[i] & 2u) {
-						int en = (int)(sq[i] >> 1) + 1, st = en - (int)(sm[i] >> 8);
-						if (st > rep_en) { rep_len += rep_en - rep_st; rep_st = st, rep_en = en; }
-						else rep_en = en;
-					} else {
-						n_a += sn[i];
-						sv[k] = sv[i], sn[k] = sn[i], sq[k] = sq[i], sm[k] = sm[i];
-						++k;
-					}
-				}
-				rep_len += rep_en - rep_st;
-				n_m = k;
+			/* 32 seeds per step.  Kept seeds are compacted in place (a seed moves to an index <= its own, and every lane
+			 * has read its seed before any lane writes).  rep_len is the length of the union of the dropped seeds'
+			 * query intervals [en - span, en); en ascends, so upstream's running (rep_st, rep_en) closes a segment
+			 * exactly when a dropped seed starts after the previous dropped seed's end:
+			 * rep_len = en(last dropped) + sum over those seeds of (previous en - st). */
+			int k = 0, carry_en = 0, acc = 0;
+			unsigned na = 0;
+			for (int i0 = 0; i0 < n_m0; i0 += 32) {
+				const int i = i0 + lane;
+				const bool in = i < n_m0;
+				uint64_t v = 0;
+				uint32_t nn = 0, qq = 0, mm = 0;
+				if (in) v = sv[i], nn = sn[i], qq = sq[i], mm = sm[i];
+				const bool flg = in && (mm & 2u), kp = in && !(mm & 2u);
+				const uint32_t fm = __ballot_sync(MMG_FULL, flg), km = __ballot_sync(MMG_FULL, kp);
+				const int en = (int)(qq >> 1) + 1, st = en - (int)(mm >> 8);
+				const uint32_t below = fm & lt;
+				int pen = __shfl_sync(MMG_FULL, en, below ? 31 - __clz((int)below) : 0);
+				if (!below) pen = carry_en;
+				if (flg && st > pen) acc += pen - st;
+				if (fm) carry_en = __shfl_sync(MMG_FULL, en, 31 - __clz((int)fm));
+				__syncwarp();
+				if (kp) { const int d = k + __popc(km & lt); sv[d] = v, sn[d] = nn, sq[d] = qq, sm[d] = mm; na += nn; }
+				k += __popc(km);
+				__syncwarp();
 			}
-			n_m = __shfl_sync(MMG_FULL, n_m, 0);
-			rep_len = __shfl_sync(MMG_FULL, rep_len, 0);
-			n_a = __shfl_sync(MMG_FULL, n_a, 0);
+			rep_len = __reduce_add_sync(MMG_FULL, acc) + carry_en;
+			n_m = k;
+			n_a = __reduce_add_sync(MMG_FULL, na);
 		} else {
 			unsigned s = 0;
 			for (int i = lane; i < n_m0; i += 32) s += sn[i];
