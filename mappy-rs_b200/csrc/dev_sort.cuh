@@ -237,6 +237,7 @@ static __device__ void dev_radix_passes_cta(uint64_t *x, YT *y, int n, int *bkt_
 					atomicExch(&ctl[0], 0);
 					if (got) break;
 				}
+				__nanosleep(128); /* nothing to take yet: leave the issue slots to the warps that are permuting */
 			}
 		}
 		got = __shfl_sync(MMG_FULL, got, 0);
