@@ -259,9 +259,8 @@ static void mm_align_pair(const mm_mapopt_t *opt, int qlen, const uint8_t *qseq,
 		ksw_reset_extz(ez);
 		ez->zdropped = 1;
 	} else if (opt->q == opt->q2 && opt->e == opt->e2) {
-		/* ksw_extz2_sse: single affine gap. With q2 == q and e2 == e the dual-gap recurrences compute the same
-		 * H/E/F; upstream's separate kernel is outside the presets on this path (map-ont, map-hifi). */
-		ksw_extd2(qlen, qseq, tlen, tseq, 5, mat, opt->q, opt->e, opt->q2, opt->e2, w, zdrop, end_bonus, flag, ez, st ? &st->n_cell : 0);
+		/* single affine gap: upstream's separate kernel (a 4-tuple `scoring`, /root/reference/src/lib.rs:369-376) */
+		ksw_extz2(qlen, qseq, tlen, tseq, 5, mat, opt->q, opt->e, w, zdrop, end_bonus, flag, ez, st ? &st->n_cell : 0);
 	} else
 		ksw_extd2(qlen, qseq, tlen, tseq, 5, mat, opt->q, opt->e, opt->q2, opt->e2, w, zdrop, end_bonus, flag, ez, st ? &st->n_cell : 0);
 }

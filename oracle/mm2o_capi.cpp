@@ -200,7 +200,7 @@ mm2o_result_t *mm2o_map_batch(mm2o_aligner_t *al, const char *seqs, const uint64
 				if (regs[j].p) {
 					hits[i][j].cigar_off = cig[i].size();
 					cig[i].insert(cig[i].end(), regs[j].p->cigar.begin(), regs[j].p->cigar.end());
-					if (want_cs) css[i].push_back(mm_gen_cs(al->mi, &regs[j], s.c_str(), 1));
+					if (want_cs) css[i].push_back(want_cs == 2 ? mm_gen_MD(al->mi, &regs[j], s.c_str()) : mm_gen_cs(al->mi, &regs[j], s.c_str(), want_cs == 3 ? 0 : 1)); /* 1 short cs, 2 MD, 3 long cs */
 				} else if (want_cs) css[i].push_back(std::string());
 			}
 			mm_free_regs(regs, n_regs);
@@ -246,6 +246,9 @@ const uint32_t *mm2o_result_cigar(mm2o_result_t *r) { return r->cigar.data(); }
 const uint64_t *mm2o_result_cs_off(mm2o_result_t *r) { return r->cs_off.data(); }
 const char *mm2o_result_cs(mm2o_result_t *r) { return r->cs.c_str(); }
 void mm2o_result_stats(mm2o_result_t *r, uint64_t *out) { memcpy(out, &r->stats, sizeof(mm2o_stats_t)); }
+extern int mm2o_ksw_force_scalar;
+/* 1 = ksw_extd2 walks its 16-lane blocks byte by byte instead of using the SSE intrinsics (self-check of the oracle) */
+void mm2o_set_ksw_scalar(int v) { mm2o_ksw_force_scalar = v; }
 int mm2o_sizeof_hit(void) { return (int)sizeof(mm2o_hit_t); }
 void mm2o_result_free(mm2o_result_t *r) { delete r; }
 

@@ -18,7 +18,12 @@
 #include <string.h>
 #include <assert.h>
 #include <vector>
+#include <emmintrin.h>
+#include <smmintrin.h>
 #include "mm2o_ksw2.h"
+
+/* 1 = run the byte-by-byte restatement of the SSE blocks instead of the intrinsics (tests compare the two) */
+int mm2o_ksw_force_scalar = 0;
 
 void ksw_reset_extz(ksw_extz_t *ez)
 {
@@ -80,9 +85,14 @@ static void ksw_backtrack_rot(int is_rev, const uint8_t *p, const int *off, cons
 
 #define I8(v) ((int8_t)(v))
 
+/* The 16-lane blocks of ksw_extd2_sse are evaluated with the same SSE2/SSE4.1 instructions upstream uses
+ * (what SIMDe maps to natively on x86-64, Cargo.toml:24) unless mm2o_ksw_force_scalar is set, in which case the
+ * blocks are walked byte by byte with wrapping int8 arithmetic: the two must agree bit for bit
+ * (tests/test_oracle_fixtures.py::test_ksw_sse_blocks_equal_scalar_restatement). */
 void ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
                int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez, uint64_t *n_cell)
 {
+	const bool use_sse = !mm2o_ksw_force_scalar;
 	int r, t, qe = q + e, n_col_, tlen_, qlen_, last_st, last_en, wl, wr, max_sc, min_sc, long_thres, long_diff;
 	int with_cigar = !(flag & KSW_EZ_SCORE_ONLY), approx_max = !!(flag & KSW_EZ_APPROX_MAX);
 	int32_t H0 = 0, last_H0_t = 0;
@@ -173,6 +183,17 @@ void ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, 
 			u[r] = r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2;
 		}
 		// loop fission: set scores first (16 lanes at a time from st0; lanes past en0 are written too)
+		if (use_sse && !(flag & KSW_EZ_GENERIC_SC)) {
+			const __m128i m1_ = _mm_set1_epi8(m1), sc_mch_ = _mm_set1_epi8(sc_mch), sc_mis_ = _mm_set1_epi8(sc_mis), sc_N_ = _mm_set1_epi8(sc_N);
+			for (t = st0; t <= en0; t += 16) {
+				__m128i sq = _mm_loadu_si128((const __m128i*)&sf[t]), st_ = _mm_loadu_si128((const __m128i*)&qrr[t]);
+				__m128i mask = _mm_or_si128(_mm_cmpeq_epi8(sq, m1_), _mm_cmpeq_epi8(st_, m1_));
+				__m128i tmp = _mm_cmpeq_epi8(sq, st_);
+				tmp = _mm_blendv_epi8(sc_mis_, sc_mch_, tmp);
+				tmp = _mm_blendv_epi8(tmp, sc_N_, mask);
+				_mm_storeu_si128((__m128i*)((int8_t*)s + t), tmp);
+			}
+		} else
 		for (t = st0; t <= en0; t += 16) {
 			for (int k = 0; k < 16; ++k) {
 				const uint8_t *psq = &sf[t + k], *pst = &qrr[t + k];
@@ -192,6 +213,87 @@ void ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, 
 			off[r] = st, off_end[r] = en;
 			uint8_t *pr = p.data() + (size_t)r * n_col - st;
 			int8_t px = x1, px2 = x21, pv = v1;
+			if (use_sse) {
+				const __m128i q_ = _mm_set1_epi8(q), q2_ = _mm_set1_epi8(q2), qe_ = _mm_set1_epi8(qe), qe2_ = _mm_set1_epi8(qe2), zero_ = _mm_setzero_si128();
+				const __m128i sc_mch_ = _mm_set1_epi8(sc_mch);
+				__m128i x1_ = _mm_cvtsi32_si128((uint8_t)x1), x21_ = _mm_cvtsi32_si128((uint8_t)x21), v1_ = _mm_cvtsi32_si128((uint8_t)v1);
+				const bool right = (flag & KSW_EZ_RIGHT) != 0;
+				for (t = st; t <= en; t += 16) {
+					__m128i d, z, a, b, a2, b2, xt1, x2t1, vt1, ut, tmp;
+					z = _mm_loadu_si128((const __m128i*)(s + t));
+					xt1 = _mm_loadu_si128((const __m128i*)(x + t));
+					tmp = _mm_srli_si128(xt1, 15);
+					xt1 = _mm_or_si128(_mm_slli_si128(xt1, 1), x1_);
+					x1_ = tmp;
+					vt1 = _mm_loadu_si128((const __m128i*)(v + t));
+					tmp = _mm_srli_si128(vt1, 15);
+					vt1 = _mm_or_si128(_mm_slli_si128(vt1, 1), v1_);
+					v1_ = tmp;
+					a = _mm_add_epi8(xt1, vt1);
+					ut = _mm_loadu_si128((const __m128i*)(u + t));
+					b = _mm_add_epi8(_mm_loadu_si128((const __m128i*)(y + t)), ut);
+					x2t1 = _mm_loadu_si128((const __m128i*)(x2 + t));
+					tmp = _mm_srli_si128(x2t1, 15);
+					x2t1 = _mm_or_si128(_mm_slli_si128(x2t1, 1), x21_);
+					x21_ = tmp;
+					a2 = _mm_add_epi8(x2t1, vt1);
+					b2 = _mm_add_epi8(_mm_loadu_si128((const __m128i*)(y2 + t)), ut);
+					if (!right) {
+						d = _mm_and_si128(_mm_cmpgt_epi8(a, z), _mm_set1_epi8(1));
+						z = _mm_max_epi8(z, a);
+						d = _mm_blendv_epi8(d, _mm_set1_epi8(2), _mm_cmpgt_epi8(b, z));
+						z = _mm_max_epi8(z, b);
+						d = _mm_blendv_epi8(d, _mm_set1_epi8(3), _mm_cmpgt_epi8(a2, z));
+						z = _mm_max_epi8(z, a2);
+						d = _mm_blendv_epi8(d, _mm_set1_epi8(4), _mm_cmpgt_epi8(b2, z));
+						z = _mm_max_epi8(z, b2);
+					} else {
+						d = _mm_andnot_si128(_mm_cmpgt_epi8(z, a), _mm_set1_epi8(1));
+						z = _mm_max_epi8(z, a);
+						d = _mm_blendv_epi8(_mm_set1_epi8(2), d, _mm_cmpgt_epi8(z, b));
+						z = _mm_max_epi8(z, b);
+						d = _mm_blendv_epi8(_mm_set1_epi8(3), d, _mm_cmpgt_epi8(z, a2));
+						z = _mm_max_epi8(z, a2);
+						d = _mm_blendv_epi8(_mm_set1_epi8(4), d, _mm_cmpgt_epi8(z, b2));
+						z = _mm_max_epi8(z, b2);
+					}
+					z = _mm_min_epi8(z, sc_mch_);
+					_mm_storeu_si128((__m128i*)(u + t), _mm_sub_epi8(z, vt1));
+					_mm_storeu_si128((__m128i*)(v + t), _mm_sub_epi8(z, ut));
+					tmp = _mm_sub_epi8(z, q_);
+					a = _mm_sub_epi8(a, tmp), b = _mm_sub_epi8(b, tmp);
+					tmp = _mm_sub_epi8(z, q2_);
+					a2 = _mm_sub_epi8(a2, tmp), b2 = _mm_sub_epi8(b2, tmp);
+					if (!right) {
+						tmp = _mm_cmpgt_epi8(a, zero_);
+						_mm_storeu_si128((__m128i*)(x + t), _mm_sub_epi8(_mm_and_si128(tmp, a), qe_));
+						d = _mm_or_si128(d, _mm_and_si128(tmp, _mm_set1_epi8(0x08)));
+						tmp = _mm_cmpgt_epi8(b, zero_);
+						_mm_storeu_si128((__m128i*)(y + t), _mm_sub_epi8(_mm_and_si128(tmp, b), qe_));
+						d = _mm_or_si128(d, _mm_and_si128(tmp, _mm_set1_epi8(0x10)));
+						tmp = _mm_cmpgt_epi8(a2, zero_);
+						_mm_storeu_si128((__m128i*)(x2 + t), _mm_sub_epi8(_mm_and_si128(tmp, a2), qe2_));
+						d = _mm_or_si128(d, _mm_and_si128(tmp, _mm_set1_epi8(0x20)));
+						tmp = _mm_cmpgt_epi8(b2, zero_);
+						_mm_storeu_si128((__m128i*)(y2 + t), _mm_sub_epi8(_mm_and_si128(tmp, b2), qe2_));
+						d = _mm_or_si128(d, _mm_and_si128(tmp, _mm_set1_epi8(0x40)));
+					} else {
+						tmp = _mm_cmpgt_epi8(zero_, a);
+						_mm_storeu_si128((__m128i*)(x + t), _mm_sub_epi8(_mm_andnot_si128(tmp, a), qe_));
+						d = _mm_or_si128(d, _mm_andnot_si128(tmp, _mm_set1_epi8(0x08)));
+						tmp = _mm_cmpgt_epi8(zero_, b);
+						_mm_storeu_si128((__m128i*)(y + t), _mm_sub_epi8(_mm_andnot_si128(tmp, b), qe_));
+						d = _mm_or_si128(d, _mm_andnot_si128(tmp, _mm_set1_epi8(0x10)));
+						tmp = _mm_cmpgt_epi8(zero_, a2);
+						_mm_storeu_si128((__m128i*)(x2 + t), _mm_sub_epi8(_mm_andnot_si128(tmp, a2), qe2_));
+						d = _mm_or_si128(d, _mm_andnot_si128(tmp, _mm_set1_epi8(0x20)));
+						tmp = _mm_cmpgt_epi8(zero_, b2);
+						_mm_storeu_si128((__m128i*)(y2 + t), _mm_sub_epi8(_mm_andnot_si128(tmp, b2), qe2_));
+						d = _mm_or_si128(d, _mm_andnot_si128(tmp, _mm_set1_epi8(0x40)));
+					}
+					_mm_storeu_si128((__m128i*)(pr + t), d);
+				}
+			} else
 			for (t = st; t <= en; ++t) {
 				int8_t z, a, b, a2, b2, xt1, x2t1, vt1, ut, tmp;
 				uint8_t d;
@@ -294,6 +396,21 @@ void ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, 
 				max_H = H[en0] = en0 > 0 ? H[en0 - 1] + u[en0] : H[en0] + v[en0]; // special casing the last element
 				max_t = en0;
 				for (i = 0; i < 4; ++i) HH[i] = max_H, tt[i] = max_t;
+				if (use_sse) {
+					__m128i max_H_ = _mm_set1_epi32(max_H), max_t_ = _mm_set1_epi32(max_t);
+					for (t = st0; t < en1; t += 4) {
+						__m128i H1 = _mm_loadu_si128((const __m128i*)&H[t]);
+						int32_t v4;
+						memcpy(&v4, v + t, 4);
+						H1 = _mm_add_epi32(H1, _mm_cvtepi8_epi32(_mm_cvtsi32_si128(v4)));
+						_mm_storeu_si128((__m128i*)&H[t], H1);
+						const __m128i tmp = _mm_cmpgt_epi32(H1, max_H_);
+						max_H_ = _mm_blendv_epi8(max_H_, H1, tmp);
+						max_t_ = _mm_blendv_epi8(max_t_, _mm_set1_epi32(t), tmp);
+					}
+					_mm_storeu_si128((__m128i*)HH, max_H_);
+					_mm_storeu_si128((__m128i*)tt, max_t_);
+				} else
 				for (t = st0; t < en1; t += 4) { // this implements: H[t]+=v8[t]-qe; if(H[t]>max_H) max_H=H[t],max_t=t;
 					for (i = 0; i < 4; ++i) {
 						H[t + i] += (int32_t)v[t + i];
@@ -330,6 +447,211 @@ void ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, 
 				}
 			} else H0 = v[0] - qe, last_H0_t = 0;
 			if ((flag & KSW_EZ_APPROX_DROP) && ksw_apply_zdrop(ez, 1, H0, r, last_H0_t, zdrop, e2)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1)
+				ez->score = H0;
+		}
+		last_st = st, last_en = en;
+	}
+	if (with_cigar) { // backtrack
+		int rev_cigar = !!(flag & KSW_EZ_REV_CIGAR);
+		if (!ez->zdropped && !(flag & KSW_EZ_EXTZ_ONLY)) {
+			ksw_backtrack_rot(rev_cigar, p.data(), off.data(), off_end.data(), n_col, tlen - 1, qlen - 1, ez->cigar);
+		} else if (!ez->zdropped && (flag & KSW_EZ_EXTZ_ONLY) && ez->mqe + end_bonus > (int)ez->max) {
+			ez->reach_end = 1;
+			ksw_backtrack_rot(rev_cigar, p.data(), off.data(), off_end.data(), n_col, ez->mqe_t, qlen - 1, ez->cigar);
+		} else if (ez->max_t >= 0 && ez->max_q >= 0) {
+			ksw_backtrack_rot(rev_cigar, p.data(), off.data(), off_end.data(), n_col, ez->max_t, ez->max_q, ez->cigar);
+		}
+	}
+}
+
+/* ksw2_extz2_sse.c: ksw_extz2_sse -- the single-affine kernel mm_align_pair dispatches to when q == q2 and
+ * e == e2, which is what a 4-tuple `scoring` gives (/root/reference/src/lib.rs:369-376 sets q2 = q, e2 = e).
+ * Upstream keeps u, v, x, y SHIFTED by q+e (z by 2(q+e)) so that every value is a non-negative byte and unsigned
+ * max/min apply; restated here with the same intrinsics.  The device runs its dual-gap kernel with equal gap
+ * pairs for this case; tests/test_emu_parity.py and tests/test_gpu_parity.py check that the two agree. */
+void ksw_extz2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
+               int8_t q, int8_t e, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez, uint64_t *n_cell)
+{
+	int r, t, qe = q + e, n_col_, tlen_, qlen_, last_st, last_en, wl, wr, max_sc, min_sc;
+	const int with_cigar = !(flag & KSW_EZ_SCORE_ONLY), approx_max = !!(flag & KSW_EZ_APPROX_MAX);
+	int32_t H0 = 0, last_H0_t = 0;
+
+	ksw_reset_extz(ez);
+	if (m <= 0 || qlen <= 0 || tlen <= 0) return;
+	const __m128i zero_ = _mm_set1_epi8(0), q_ = _mm_set1_epi8(q), qe2_ = _mm_set1_epi8((q + e) * 2);
+	const __m128i flag1_ = _mm_set1_epi8(1), flag2_ = _mm_set1_epi8(2), flag8_ = _mm_set1_epi8(0x08), flag16_ = _mm_set1_epi8(0x10);
+	const __m128i sc_mch_ = _mm_set1_epi8(mat[0]), sc_mis_ = _mm_set1_epi8(mat[1]);
+	const __m128i sc_N_ = mat[m * m - 1] == 0 ? _mm_set1_epi8(-e) : _mm_set1_epi8(mat[m * m - 1]);
+	const __m128i m1_ = _mm_set1_epi8(m - 1), max_sc_ = _mm_set1_epi8(mat[0] + (q + e) * 2);
+
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	wl = wr = w;
+	tlen_ = (tlen + 15) / 16;
+	n_col_ = qlen < tlen ? qlen : tlen;
+	n_col_ = ((n_col_ < w + 1 ? n_col_ : w + 1) + 15) / 16 + 1;
+	qlen_ = (qlen + 15) / 16;
+	for (t = 1, max_sc = mat[0], min_sc = mat[1]; t < m * m; ++t) {
+		max_sc = max_sc > mat[t] ? max_sc : mat[t];
+		min_sc = min_sc < mat[t] ? min_sc : mat[t];
+	}
+	if (-min_sc > 2 * (q + e)) return; // otherwise, we won't see any mismatches
+
+	/* kcalloc(tlen_ * 6 + qlen_ + 1, 16): u, v, x, y, s, sf, qr back to back, zero = the shifted form of -q-e */
+	const size_t T16 = (size_t)tlen_ * 16, mem_sz = ((size_t)tlen_ * 6 + qlen_ + 1) * 16;
+	std::vector<uint8_t> mem(mem_sz + 64, 0);
+	uint8_t *u8 = mem.data(), *v8 = u8 + T16, *x8 = v8 + T16, *y8 = x8 + T16, *s8 = y8 + T16, *sf = s8 + T16, *qr = sf + T16;
+	std::vector<int32_t> H;
+	if (!approx_max) H.assign(T16, KSW_NEG_INF);
+	std::vector<uint8_t> p;
+	std::vector<int> off, off_end;
+	const int n_col = n_col_ * 16;
+	if (with_cigar) {
+		p.assign(((size_t)(qlen + tlen - 1) * n_col_ + 1) * 16, 0);
+		off.assign(qlen + tlen - 1, 0);
+		off_end.assign(qlen + tlen - 1, 0);
+	}
+	for (t = 0; t < qlen; ++t) qr[t] = query[qlen - 1 - t];
+	memcpy(sf, target, tlen);
+
+	for (r = 0, last_st = last_en = -1; r < qlen + tlen - 1; ++r) {
+		int st = 0, en = tlen - 1, st0, en0;
+		uint8_t x1, v1;
+		const uint8_t *qrr = qr + (qlen - 1 - r);
+		if (st < r - qlen + 1) st = r - qlen + 1;
+		if (en > r) en = r;
+		if (st < (r - wr + 1) >> 1) st = (r - wr + 1) >> 1; // take the ceil
+		if (en > (r + wl) >> 1) en = (r + wl) >> 1; // take the floor
+		if (st > en) {
+			ez->zdropped = 1;
+			break;
+		}
+		st0 = st, en0 = en;
+		st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;
+		// set boundary conditions
+		if (st > 0) {
+			if (st - 1 >= last_st && st - 1 <= last_en)
+				x1 = x8[st - 1], v1 = v8[st - 1]; // (r-1,s-1) calculated in the last round
+			else x1 = v1 = 0; // not calculated; set to zeros
+		} else x1 = 0, v1 = r ? q : 0;
+		if (en >= r) y8[r] = 0, u8[r] = r ? q : 0;
+		// loop fission: set scores first
+		for (t = st0; t <= en0; t += 16) {
+			__m128i sq = _mm_loadu_si128((const __m128i*)&sf[t]), st_ = _mm_loadu_si128((const __m128i*)&qrr[t]);
+			__m128i mask = _mm_or_si128(_mm_cmpeq_epi8(sq, m1_), _mm_cmpeq_epi8(st_, m1_));
+			__m128i tmp = _mm_cmpeq_epi8(sq, st_);
+			tmp = _mm_blendv_epi8(sc_mis_, sc_mch_, tmp);
+			tmp = _mm_blendv_epi8(tmp, sc_N_, mask);
+			_mm_storeu_si128((__m128i*)(s8 + t), tmp);
+		}
+		// core loop
+		__m128i x1_ = _mm_cvtsi32_si128(x1), v1_ = _mm_cvtsi32_si128(v1);
+		uint8_t *pr = with_cigar ? p.data() + (size_t)r * n_col - st : 0;
+		if (with_cigar) off[r] = st, off_end[r] = en;
+		const bool right = (flag & KSW_EZ_RIGHT) != 0;
+		for (t = st; t <= en; t += 16) {
+			__m128i d = zero_, z, a, b, xt1, vt1, ut, tmp;
+			z = _mm_add_epi8(_mm_loadu_si128((const __m128i*)(s8 + t)), qe2_);
+			xt1 = _mm_loadu_si128((const __m128i*)(x8 + t));
+			tmp = _mm_srli_si128(xt1, 15);
+			xt1 = _mm_or_si128(_mm_slli_si128(xt1, 1), x1_);
+			x1_ = tmp;
+			vt1 = _mm_loadu_si128((const __m128i*)(v8 + t));
+			tmp = _mm_srli_si128(vt1, 15);
+			vt1 = _mm_or_si128(_mm_slli_si128(vt1, 1), v1_);
+			v1_ = tmp;
+			a = _mm_add_epi8(xt1, vt1);
+			ut = _mm_loadu_si128((const __m128i*)(u8 + t));
+			b = _mm_add_epi8(_mm_loadu_si128((const __m128i*)(y8 + t)), ut);
+			if (!with_cigar) {
+				z = _mm_max_epi8(z, a);
+			} else if (!right) {
+				d = _mm_and_si128(_mm_cmpgt_epi8(a, z), flag1_);       // d = a > z? 1 : 0
+				z = _mm_max_epi8(z, a);
+				tmp = _mm_cmpgt_epi8(b, z);
+				d = _mm_blendv_epi8(d, flag2_, tmp);                   // d = b > z? 2 : d
+			} else {
+				d = _mm_andnot_si128(_mm_cmpgt_epi8(z, a), flag1_);    // d = z > a? 0 : 1
+				z = _mm_max_epi8(z, a);
+				tmp = _mm_cmpgt_epi8(z, b);
+				d = _mm_blendv_epi8(flag2_, d, tmp);                   // d = z > b? d : 2
+			}
+			z = _mm_max_epu8(z, b);
+			z = _mm_min_epu8(z, max_sc_);
+			_mm_storeu_si128((__m128i*)(u8 + t), _mm_sub_epi8(z, vt1));
+			_mm_storeu_si128((__m128i*)(v8 + t), _mm_sub_epi8(z, ut));
+			z = _mm_sub_epi8(z, q_);
+			a = _mm_sub_epi8(a, z);
+			b = _mm_sub_epi8(b, z);
+			if (!with_cigar || !right) {
+				tmp = _mm_cmpgt_epi8(a, zero_);
+				_mm_storeu_si128((__m128i*)(x8 + t), _mm_and_si128(tmp, a));
+				d = _mm_or_si128(d, _mm_and_si128(tmp, flag8_));       // d = a > 0? 0x08 : 0
+				tmp = _mm_cmpgt_epi8(b, zero_);
+				_mm_storeu_si128((__m128i*)(y8 + t), _mm_and_si128(tmp, b));
+				d = _mm_or_si128(d, _mm_and_si128(tmp, flag16_));      // d = b > 0? 0x10 : 0
+			} else {
+				tmp = _mm_cmpgt_epi8(zero_, a);
+				_mm_storeu_si128((__m128i*)(x8 + t), _mm_andnot_si128(tmp, a));
+				d = _mm_or_si128(d, _mm_andnot_si128(tmp, flag8_));    // d = 0 > a? 0 : 0x08
+				tmp = _mm_cmpgt_epi8(zero_, b);
+				_mm_storeu_si128((__m128i*)(y8 + t), _mm_andnot_si128(tmp, b));
+				d = _mm_or_si128(d, _mm_andnot_si128(tmp, flag16_));   // d = 0 > b? 0 : 0x10
+			}
+			if (with_cigar) _mm_storeu_si128((__m128i*)(pr + t), d);
+		}
+		if (n_cell) *n_cell += en0 - st0 + 1;
+		if (!approx_max) { // find the exact max with a 32-bit score array
+			int32_t max_H, max_t;
+			if (r > 0) {
+				int32_t HH[4], tt[4], en1 = st0 + (en0 - st0) / 4 * 4, i;
+				max_H = H[en0] = en0 > 0 ? H[en0 - 1] + u8[en0] - qe : H[en0] + v8[en0] - qe; // special casing the last element
+				max_t = en0;
+				__m128i max_H_ = _mm_set1_epi32(max_H), max_t_ = _mm_set1_epi32(max_t);
+				const __m128i qe_ = _mm_set1_epi32(q + e);
+				for (t = st0; t < en1; t += 4) { // this implements: H[t]+=v8[t]-qe; if(H[t]>max_H) max_H=H[t],max_t=t;
+					__m128i H1 = _mm_loadu_si128((const __m128i*)&H[t]);
+					__m128i t_ = _mm_setr_epi32(v8[t], v8[t + 1], v8[t + 2], v8[t + 3]);
+					H1 = _mm_add_epi32(H1, t_);
+					H1 = _mm_sub_epi32(H1, qe_);
+					_mm_storeu_si128((__m128i*)&H[t], H1);
+					t_ = _mm_set1_epi32(t);
+					const __m128i tmp = _mm_cmpgt_epi32(H1, max_H_);
+					max_H_ = _mm_blendv_epi8(max_H_, H1, tmp);
+					max_t_ = _mm_blendv_epi8(max_t_, t_, tmp);
+				}
+				_mm_storeu_si128((__m128i*)HH, max_H_);
+				_mm_storeu_si128((__m128i*)tt, max_t_);
+				for (i = 0; i < 4; ++i)
+					if (max_H < HH[i]) max_H = HH[i], max_t = tt[i] + i;
+				for (; t < en0; ++t) { // for the rest of values that haven't been computed with SSE
+					H[t] += (int32_t)v8[t] - qe;
+					if (H[t] > max_H)
+						max_H = H[t], max_t = t;
+				}
+			} else H[0] = v8[0] - qe - qe, max_H = H[0], max_t = 0; // special casing r==0
+			// update ez
+			if (en0 == tlen - 1 && H[en0] > ez->mte)
+				ez->mte = H[en0], ez->mte_q = r - en;
+			if (r - st0 == qlen - 1 && H[st0] > ez->mqe)
+				ez->mqe = H[st0], ez->mqe_t = st0;
+			if (ksw_apply_zdrop(ez, 1, max_H, r, max_t, zdrop, e)) break;
+			if (r == qlen + tlen - 2 && en0 == tlen - 1)
+				ez->score = H[tlen - 1];
+		} else { // find approximate max; Z-drop might be inaccurate, too.
+			if (r > 0) {
+				if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+					int32_t d0 = v8[last_H0_t] - qe;
+					int32_t d1 = u8[last_H0_t + 1] - qe;
+					if (d0 > d1) H0 += d0;
+					else H0 += d1, ++last_H0_t;
+				} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+					H0 += v8[last_H0_t] - qe;
+				} else {
+					++last_H0_t, H0 += u8[last_H0_t] - qe;
+				}
+				if ((flag & KSW_EZ_APPROX_DROP) && ksw_apply_zdrop(ez, 1, H0, r, last_H0_t, zdrop, e)) break;
+			} else H0 = v8[0] - qe - qe, last_H0_t = 0;
 			if (r == qlen + tlen - 2 && en0 == tlen - 1)
 				ez->score = H0;
 		}

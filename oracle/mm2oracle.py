@@ -65,6 +65,7 @@ def lib():
         getattr(L, nm).restype = vp; getattr(L, nm).argtypes = [vp]
     L.mm2o_result_stats.argtypes = [vp, vp]
     L.mm2o_result_free.argtypes = [vp]
+    L.mm2o_set_ksw_scalar.argtypes = [i32]
     L.mm2o_trace.restype = vp; L.mm2o_trace.argtypes = [vp, cp, i32]
     L.mm2o_trace_n.restype = u64; L.mm2o_trace_n.argtypes = [vp, i32]
     L.mm2o_trace_ptr.restype = vp; L.mm2o_trace_ptr.argtypes = [vp, i32]

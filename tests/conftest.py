@@ -23,6 +23,11 @@ PRODUCT_LIB = os.path.join(PKG, "libmmg.so")
 EMU_LIB = os.path.join(ROOT, "tests", "emu", "libmmg_emu.so")
 
 
+# the reference's own test file is kept verbatim under tests/golden/reference_tests and is run, unchanged, by
+# tests/test_reference_pytests.py in a separate pytest process against mappy-rs_b200/mappy_rs (GPU box only)
+collect_ignore_glob = ["golden/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

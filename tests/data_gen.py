@@ -135,3 +135,62 @@ def make_sv_reads(seed, ref, coff, n_reads, len_min=400, len_max=4000):
     offs = np.zeros(len(bs) + 1, dtype=np.uint64)
     offs[1:] = np.cumsum([len(b) for b in bs])
     return np.frombuffer(b"".join(bs), dtype=np.uint8).copy(), offs
+
+
+def config0_reads(contigs, n_reads=20000, seed=20261018, len_min=1000, len_max=10000, err=0.08, n_frac=0.0):
+    """BASELINE.json configs[0]: the reference's 4 x 400 bp fixture cannot host 1-10 kb reads,
+    so every read is random flank + a substring of a contig (200-400 bp, random contig and strand, `err` errors
+    split 3:2:3 into substitutions / insertions / deletions) + random flank.  `contigs`: list of str."""
+    rs = np.random.RandomState(seed % (2 ** 32))
+    comp = str.maketrans("ACGT", "TGCA")
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    p_sub, p_ins, p_del = err * 3 / 8, err * 2 / 8, err * 3 / 8
+    out = []
+    for _ in range(n_reads):
+        total = int(rs.randint(len_min, len_max + 1))
+        ctg = contigs[rs.randint(len(contigs))]
+        sl = int(rs.randint(200, min(400, len(ctg)) + 1))
+        st = int(rs.randint(0, len(ctg) - sl + 1))
+        core = ctg[st:st + sl]
+        if rs.randint(2):
+            core = core.translate(comp)[::-1]
+        c = np.frombuffer(core.encode(), dtype=np.uint8)
+        u = rs.random_sample(len(c))
+        pieces = []
+        for b, x in zip(c.tolist(), u.tolist()):
+            if x < p_del:
+                continue
+            if x < p_del + p_sub:
+                b = int(acgt[(b"ACGT".find(bytes([b])) + 1 + rs.randint(3)) % 4]) if bytes([b]) in b"ACGT" else b
+            pieces.append(b)
+            if x > 1.0 - p_ins:
+                pieces.append(int(acgt[rs.randint(4)]))
+        core_b = bytes(pieces)
+        left = int(rs.randint(0, max(1, total - len(core_b))))
+        right = max(0, total - len(core_b) - left)
+        s = acgt[rs.randint(0, 4, left)].tobytes() + core_b + acgt[rs.randint(0, 4, right)].tobytes()
+        if n_frac > 0:
+            a = np.frombuffer(s, dtype=np.uint8).copy()
+            a[rs.random_sample(len(a)) < n_frac] = ord("N")
+            s = a.tobytes()
+        out.append(s)
+    offs = np.zeros(len(out) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(b) for b in out])
+    return np.frombuffer(b"".join(out), dtype=np.uint8).copy(), offs
+
+
+def prefixes(buf, offs, n=400):
+    """BASELINE.json configs[3]: the first `n` bases of every read (readfish-style adaptive sampling)."""
+    ln = np.minimum(np.diff(offs.astype(np.int64)), n)
+    noffs = np.zeros(len(offs), dtype=np.uint64)
+    noffs[1:] = np.cumsum(ln)
+    idx = np.repeat(offs[:-1].astype(np.int64) - noffs[:-1].astype(np.int64), ln) + np.arange(int(noffs[-1]))
+    return buf[idx].copy(), noffs
+
+
+def sprinkle_n(buf, seed, frac=0.002):
+    """A copy of the reads with a fraction of the bases replaced by N (ambiguity codes in cs / MD / sc_ambi paths)."""
+    rs = np.random.RandomState(seed)
+    a = buf.copy()
+    a[rs.random_sample(len(a)) < frac] = ord("N")
+    return a

@@ -134,3 +134,20 @@ def logf_mismatches(lib, n):
     lib.check(lib.L.mmg_debug_logf(x.ctypes.data, out.ctypes.data, len(x)))
     want = np.array([libm.logf(float(v)) for v in x], dtype=np.float32)
     return int(np.count_nonzero(out.view(np.uint32) != want.view(np.uint32)))
+
+
+def compare_tags(case, buf, offs, dev, which, limit=5):
+    """mmg_gen_tags (cs short form / MD, host marshalling of the product) against the oracle's mm_gen_cs / mm_gen_MD
+    (oracle/mm2o_align.cpp) for every hit of the batch.  which: 0 = cs (no_iden = 1, what crate minimap2 passes), 1 = MD."""
+    ours = _mmg.gen_tags(case.lib, case.index, buf, offs, dev, which)
+    ora = case.oracle.map_batch(buf, offs, 8, cs=2 if which else 1)
+    diffs = []
+    if len(ours) != len(ora.hits):
+        return ["tag count %d vs %d hits" % (len(ours), len(ora.hits))]
+    for i in range(len(ours)):
+        want = ora.cs[int(ora.cs_off[i]):int(ora.cs_off[i + 1])] if ora.hits["n_cigar"][i] else None
+        if ours[i] != want:
+            diffs.append("hit %d: %s differs: %r vs oracle %r" % (i, "MD" if which else "cs", (ours[i] or b"")[:60], (want or b"")[:60]))
+            if len(diffs) >= limit:
+                break
+    return diffs

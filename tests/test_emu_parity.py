@@ -392,3 +392,55 @@ def test_sketch_window_sizes(emu_lib, oracle_mod, k, w):
         al.close()
         idx.close()
         ora.close()
+
+
+def _fixture_contigs(oracle):
+    return [oracle.seq(n) for n in oracle.seq_names]
+
+
+def test_config0_flanked_noisy_reads_with_cigar(emu_lib, oracle_mod):
+    """BASELINE.json configs[0] in mappy-rs' real mode (CIGAR on): random flank + 8 %-error substring of a contig of
+    the reference's test.mmi + random flank; every field and CIGAR operation against the oracle."""
+    c = parity.Case(emu_lib, None, None, mmi=MMI, cigar=True)
+    try:
+        buf, offs = data_gen.config0_reads(_fixture_contigs(c.oracle), 80, len_max=3000)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_hits(dev, ora) == []
+        assert len(ora.hits) >= 50 and (ora.hits["rev"] != 0).sum() > 10 and (ora.hits["nm"] > 0).sum() > 30
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("scoring", [(2, 4, 4, 2), (1, 4, 6, 2)])
+def test_four_tuple_scoring_equals_ksw_extz2(emu_lib, oracle_mod, scoring):
+    """A 4-tuple `scoring` (/root/reference/src/lib.rs:369-376) makes q2 = q, e2 = e, and upstream then runs
+    ksw_extz2_sse.  The oracle restates that kernel separately (oracle/mm2o_ksw2.cpp ksw_extz2); the device runs its
+    dual-gap kernel with equal gap pairs and must produce the same CIGARs and scores."""
+    ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
+    a, b, q, e = scoring
+    c = parity.Case(emu_lib, names, seqs, cigar=True, overrides=dict(a=a, b=b, q=q, e=e, q2=q, e2=e))
+    try:
+        buf, offs = data_gen.make_sv_reads(57, ref, coff, 40)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_hits(dev, ora) == []
+        assert (ora.hits["n_cigar"] > 3).sum() > 15
+    finally:
+        c.close()
+
+
+def test_cs_and_md_tags_match_oracle(emu_lib, oracle_mod):
+    """cs (short form, what map_batch always returns: /root/reference/src/lib.rs:589) and MD of every hit against the
+    oracle's mm_gen_cs / mm_gen_MD on noisy reads of both strands that contain N bases."""
+    ref, coff, names, seqs = parity.random_reference(61, [200000])
+    c = parity.Case(emu_lib, names, seqs, cigar=True)
+    try:
+        buf, offs, truth = data_gen.make_reads(62, ref, coff, 60, 300, 3000)
+        buf = data_gen.sprinkle_n(buf, 63, 0.004)
+        dev = c.aligner.map_batch(buf, offs)
+        assert (dev.hits["rev"] != 0).sum() > 10 and (dev.hits["rev"] == 0).sum() > 10 and (dev.hits["n_ambi"] > 0).sum() > 10
+        assert parity.compare_tags(c, buf, offs, dev, 0) == []
+        assert parity.compare_tags(c, buf, offs, dev, 1) == []
+    finally:
+        c.close()

@@ -229,41 +229,6 @@ def _same_hits(x, y):
     return x.shape == y.shape and all(np.array_equal(x[f], y[f]) for f in x.dtype.names)
 
 
-def test_full_size_properties_human_scale(gpu_lib):
-    """BASELINE.json configs[2] at full reference size (3.1 Gb, 24 contigs; index built on the device): properties
-    that need no oracle - simulated reads come back at their origin, results do not depend on how the batch is cut
-    into chunks, and mapping the same batch twice gives the same bytes."""
-    import ctypes
-    from mappy_rs import _mmg
-    ref, coff, names = data_gen.make_reference(3, data_gen.config2_contig_lens())
-    io, mo = _mmg.IdxOpt(), _mmg.MapOpt()
-    gpu_lib.check(gpu_lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mo)))
-    mo.flag = 0
-    idx = _mmg.Index.build(gpu_lib, io, names, [ref[int(coff[i]):int(coff[i + 1])].tobytes() for i in range(len(names))])
-    gpu_lib.check(gpu_lib.L.mmg_mapopt_update(ctypes.byref(mo), idx.h))
-    al = _mmg.DeviceAligner(gpu_lib, idx, mo)
-    try:
-        n = 60000
-        buf, offs, truth = data_gen.make_reads(4, ref, coff, n, 1000, 10000, p_sub=0.03, p_ins=0.02, p_del=0.03)
-        a = al.map_batch(buf, offs)
-        assert a.stats["n_dropped"] > 0.5 * a.stats["n_anchor"]          # the isolated-anchor filter is at work
-        p = _primary(a, n)
-        h = a.hits[np.maximum(p, 0)]
-        ok = (p >= 0) & (h["rid"] == truth[:, 0]) & (h["rev"] == (truth[:, 3] != 0)) & \
-             (np.minimum(h["re"], truth[:, 2]) - np.maximum(h["rs"], truth[:, 1]) > 0.8 * (truth[:, 2] - truth[:, 1]))
-        assert ok.mean() > 0.99, ok.mean()     # the rest: reads drawn across a contig boundary, chain ends trimmed by errors
-        assert (h["mapq"][ok] == 60).mean() > 0.98
-        b = al.map_batch(buf, offs)                                          # idempotence
-        assert np.array_equal(a.hit_off, b.hit_off) and _same_hits(a.hits, b.hits)
-        half = n // 2                                                        # two calls of half the reads each
-        c1 = al.map_batch(buf[:int(offs[half])], offs[:half + 1])
-        c2 = al.map_batch(buf[int(offs[half]):], offs[half:] - offs[half])
-        assert _same_hits(a.hits, np.concatenate([c1.hits, c2.hits]))
-    finally:
-        al.close()
-        idx.close()
-
-
 def test_reverse_complement_symmetry(case5mb):
     """A read and its reverse complement map to the same target interval on opposite strands with the same
     chain score (minimizers are canonical); 20 000 reads of configs[1]."""

@@ -110,3 +110,28 @@ def test_all_fixture_contigs_and_reverse_complements(oracle_mod):
             assert len(r.hits) == 1
             h = r.hits[0]
             assert (o.seq_names[h["rid"]], h["rs"], h["re"], h["rev"], h["mapq"]) == (name, 0, 400, rev, 60)
+
+
+def test_ksw_sse_blocks_equal_scalar_restatement(oracle_mod):
+    """The oracle evaluates ksw_extd2's 16-lane blocks with the SSE2/SSE4.1 intrinsics upstream uses (what SIMDe maps
+    to on x86-64).  The byte-by-byte restatement of the same blocks is kept as a self-check: both must give the same
+    hits and CIGARs (left- and right-aligned gaps, exact and approximate maximum, z-drop splits, inversions)."""
+    import numpy as np
+    import data_gen
+    import parity
+    ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
+    buf, offs = data_gen.make_sv_reads(57, ref, coff, 120)
+    L = oracle_mod.lib()
+    for preset in (None, "map-hifi"):
+        o = oracle_mod.Oracle(names=names, seqs=seqs, preset=preset)
+        o.set_opt("flag", 4)
+        try:
+            L.mm2o_set_ksw_scalar(1)
+            a = o.map_batch(buf, offs, 8)
+            L.mm2o_set_ksw_scalar(0)
+            b = o.map_batch(buf, offs, 8)
+        finally:
+            L.mm2o_set_ksw_scalar(0)
+            o.close()
+        assert len(a.hits) > 100 and ((a.hits["flags"] & 8) > 0).sum() > 10
+        assert all(np.array_equal(a.hits[f], b.hits[f]) for f in a.hits.dtype.names) and np.array_equal(a.cigar, b.cigar)
