@@ -206,8 +206,9 @@ void mmg_batch_destroy(mmg_batch *b);
 
 /* per-batch counters (roofline denominators):
  * n_bases, n_mz, n_seed, n_hit, n_anchor, n_iter, n_kept, n_cell, n_regs, n_rechain,
- * n_dropped (isolated anchors removed before the sort; counted in n_anchor) */
-#define MMG_N_STATS 11
+ * n_dropped (isolated anchors removed before the sort; counted in n_anchor),
+ * n_cell_fill (the cells of n_cell computed by the register-resident gap-fill kernel) */
+#define MMG_N_STATS 12
 int mmg_batch_stats(const mmg_batch *b, uint64_t out[MMG_N_STATS]);
 /* device milliseconds per pipeline stage of the last mmg_batch_run ("profile"=1) and launches */
 #define MMG_N_STAGES 12

@@ -113,6 +113,7 @@ struct ChunkDev {
 	/* counters */
 	unsigned long long *stats; /* MMG_N_STATS */
 	uint32_t *work;            /* dynamic work counters, one per kernel launch */
+	uint32_t *err;             /* one word: OR of every arena-overflow flag raised while the chunk ran (read back by the host) */
 	uint32_t *big_list;        /* reads deferred by a kernel's small-tile pass to its large-tile pass */
 	uint32_t *tie_list;        /* reads whose anchors have equal keys (sort stage) */
 	uint32_t *flags;           /* per read: bit0 = anchor ties (exact re-sort done), bit1 = re-chained, bit2 = isolated anchors dropped */

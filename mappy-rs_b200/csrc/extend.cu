@@ -389,7 +389,7 @@ ext_prep_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t r0, uint
 			if (r2.id != r2.parent && r2.parent != PARENT_TMP_PRI) ok = false;
 			if (r1.rid != r2.rid || r1rev != (int)REG_REV(r2)) ok = false;
 			if (ql < o.min_chain_score || ql > o.max_gap || tl < o.min_chain_score || tl > o.max_gap) ok = false;
-			if (ok && (uint64_t)(7 * (tl + 1) + 2) * 4 + (uint64_t)tl * 8 > xb.big_per_warp) { ok = false; if (lane == 0) atomicOr(&c.flags[r], 0x20000000u); }
+			if (ok && (uint64_t)(7 * (tl + 1) + 2) * 4 + (uint64_t)tl * 8 > xb.big_per_warp) { ok = false; if (lane == 0) atomicOr(&c.flags[r], 0x20000000u), atomicOr(c.err, 0x20000000u); }
 			int qe = -1, te = -1;
 			const int rev_inv = r1rev ? 0 : 1, p0 = r1rev ? r2.qe : qlen - r2.qs;
 			if (ok) {
@@ -409,14 +409,14 @@ ext_prep_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t r0, uint
 				if (ok) {
 					const int q_off = ql - (qe + 1), t_off = tl - (te + 1);
 					const uint32_t j0 = atomicAdd(xb.n_jobs, 1u);
-					if ((uint64_t)j0 + 1 > xb.cap_jobs) atomicOr(&c.flags[r], 0x40000000u), x->state = EXT_DONE;
+					if ((uint64_t)j0 + 1 > xb.cap_jobs) atomicOr(&c.flags[r], 0x40000000u), atomicOr(c.err, 0x40000000u), x->state = EXT_DONE;
 					else if (p0 + q_off < 0 || r1.re + t_off < 0) x->state = EXT_DONE; /* qe/te landed in the SSE padding: upstream reads before its buffers here */
 					else {
 						ExtJob *jb = &xb.jobs[j0];
 						jb->read = r, jb->reg = (uint32_t)i, jb->kind = EXT_INV, jb->rev = (uint8_t)rev_inv, jb->rid = r1.rid;
 						jb->qs = p0 + q_off, jb->qe = p0 + ql, jb->rs = r1.re + t_off, jb->re = r2.rs;
 						jb->w = (int)(o.bw * 1.5), jb->zdrop = o.zdrop, jb->end_bonus = -1, jb->flag = EZ_EXTZ_ONLY;
-						jb->n_cigar = 0, jb->zdropped = 0, jb->reach_end = 0, jb->zdrop_code = 0;
+						jb->n_cigar = 0, jb->zdropped = 0, jb->reach_end = 0, jb->zdrop_code = 0, jb->pad[0] = 0;
 						const int jq = ql - q_off, jt = tl - t_off;
 						int n_col = jq < jt ? jq : jt;
 						n_col = ((n_col < jb->w + 1 ? n_col : jb->w + 1) + 15) / 16 + 1;
@@ -450,7 +450,7 @@ ext_prep_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t r0, uint
 				if (qe_l < x->qe0 && re_l < x->re0) ++nj;
 				const uint32_t j0 = atomicAdd(xb.n_jobs, (uint32_t)nj);
 				x->job0 = j0, x->n_jobs = nj;
-				if ((uint64_t)j0 + nj > xb.cap_jobs) { atomicOr(&c.flags[r], 0x40000000u); x->n_jobs = 0; continue; }
+				if ((uint64_t)j0 + nj > xb.cap_jobs) { atomicOr(&c.flags[r], 0x40000000u), atomicOr(c.err, 0x40000000u); x->n_jobs = 0; continue; }
 				const int rid = g->rid, rev = (int)REG_REV(*g), bw = (int)(o.bw * 1.5 + 1.);
 				int bw_long = (int)(o.bw_long * 1.5 + 1.);
 				if (bw_long < bw) bw_long = bw;
@@ -459,7 +459,7 @@ ext_prep_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t r0, uint
 					ExtJob *jb = &xb.jobs[jn++];
 					jb->read = r, jb->reg = (uint32_t)i, jb->kind = (uint8_t)kind, jb->rev = (uint8_t)rev, jb->rid = rid;
 					jb->qs = qs, jb->qe = qe, jb->rs = rs, jb->re = re, jb->w = w, jb->zdrop = zdrop, jb->end_bonus = end_bonus, jb->flag = flag;
-					jb->n_cigar = 0, jb->zdropped = 0, jb->reach_end = 0, jb->zdrop_code = 0;
+					jb->n_cigar = 0, jb->zdropped = 0, jb->reach_end = 0, jb->zdrop_code = 0, jb->pad[0] = 0;
 					const int ql = qe - qs, tl = re - rs;
 					int w2 = w < 0 ? (tl > ql ? tl : ql) : w;
 					int n_col = ql < tl ? ql : tl;
@@ -481,42 +481,52 @@ ext_prep_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t r0, uint
 	}
 }
 
-/* exclusive scans of the per-job traceback / cigar sizes (single block) */
-__global__ void __launch_bounds__(1024)
-ext_job_scan_kernel(ExtBufs xb, uint32_t j0, uint32_t j1)
+/* number of jobs queued so far, clamped to the arena (prep flags the overflow); read by scan, DP and stitch */
+__device__ __forceinline__ uint32_t ext_n_jobs(const ExtBufs &xb)
 {
-	__shared__ unsigned long long s_a[32], s_b[32];
-	__shared__ unsigned long long s_ca, s_cb;
+	const uint32_t n = *xb.n_jobs;
+	return (uint64_t)n > xb.cap_jobs ? (uint32_t)xb.cap_jobs : n;
+}
+/* true when the CIGAR slices of the queued jobs fit the arena (else DP and stitch do nothing and the host reports it) */
+__device__ __forceinline__ bool ext_cigar_fits(const ExtBufs &xb) { return xb.cg_base[1] <= xb.cap_cg; }
+
+/* exclusive scan of the per-job cigar sizes of jobs [j0, *n_jobs) (single block) */
+__global__ void __launch_bounds__(1024)
+ext_job_scan_kernel(ExtBufs xb, uint32_t j0)
+{
+	__shared__ unsigned long long s_b[32];
+	__shared__ unsigned long long s_cb;
 	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
-	if (threadIdx.x == 0) s_ca = xb.tb_base[0], s_cb = xb.cg_base[0];
+	const uint32_t j1 = ext_n_jobs(xb);
+	if (threadIdx.x == 0) s_cb = xb.cg_base[0];
 	__syncthreads();
 	for (uint32_t i0 = j0; i0 < j1; i0 += 1024) {
 		uint32_t i = i0 + threadIdx.x;
-		unsigned long long va = i < j1 ? xb.jobs[i].tb_size : 0, vb = i < j1 ? xb.jobs[i].cg_size : 0, xa = va, xbv = vb;
+		unsigned long long vb = i < j1 ? xb.jobs[i].cg_size : 0, xbv = vb;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
-			unsigned long long ya = __shfl_up_sync(MMG_FULL, xa, d), yb = __shfl_up_sync(MMG_FULL, xbv, d);
-			if (lane >= d) xa += ya, xbv += yb;
+			unsigned long long yb = __shfl_up_sync(MMG_FULL, xbv, d);
+			if (lane >= d) xbv += yb;
 		}
-		if (lane == 31) s_a[wib] = xa, s_b[wib] = xbv;
+		if (lane == 31) s_b[wib] = xbv;
 		__syncthreads();
 		if (wib == 0) {
-			unsigned long long wa = s_a[lane], wb = s_b[lane], sa = wa, sb = wb;
+			unsigned long long wb = s_b[lane], sb = wb;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {
-				unsigned long long ya = __shfl_up_sync(MMG_FULL, sa, d), yb = __shfl_up_sync(MMG_FULL, sb, d);
-				if (lane >= d) sa += ya, sb += yb;
+				unsigned long long yb = __shfl_up_sync(MMG_FULL, sb, d);
+				if (lane >= d) sb += yb;
 			}
-			s_a[lane] = sa - wa, s_b[lane] = sb - wb;
+			s_b[lane] = sb - wb;
 		}
 		__syncthreads();
-		unsigned long long ca = s_ca, cb = s_cb;
-		if (i < j1) xb.jobs[i].tb_off = ca + s_a[wib] + xa - va, xb.jobs[i].cg_off = cb + s_b[wib] + xbv - vb;
+		unsigned long long cb = s_cb;
+		if (i < j1) xb.jobs[i].tb_off = 0, xb.jobs[i].cg_off = cb + s_b[wib] + xbv - vb;
 		__syncthreads();
-		if (threadIdx.x == 1023) s_ca = ca + s_a[wib] + xa, s_cb = cb + s_b[wib] + xbv;
+		if (threadIdx.x == 1023) s_cb = cb + s_b[wib] + xbv;
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) xb.tb_base[1] = s_ca, xb.cg_base[1] = s_cb;
+	if (threadIdx.x == 0) xb.cg_base[1] = s_cb;
 }
 
 /* ---------- the DP ---------- */
@@ -630,6 +640,71 @@ __device__ __forceinline__ void dp_cell2(const DpK &k, uint32_t S, uint32_t U, u
 	const uint32_t g1 = (Fb2 & 0x80008000u) | (Fa2 & 0x7fff7fffu), g2 = (Fb & 0x20002000u) | (Fa & 0xdfffdfffu);
 	const uint32_t g = (g1 & 0xc000c000u) | (g2 & 0x3fff3fffu);
 	nd |= (g >> 9) & 0x00780078u;
+}
+
+/* ---- backtrack (ksw_backtrack, is_rot = 1) from cell (i, j); returns the number of CIGAR operations ----
+ * The walk is serial, and one traceback byte per step straight from global memory costs a full L2 round trip
+ * per CIGAR base.  The warp therefore fetches a window of 32 anti-diagonals x 8 target columns below the
+ * current cell (lane = diagonal), and every lane replays the same walk out of registers (one shuffle per
+ * step) until it leaves the window: at least 8 and typically 16 steps per memory round trip.  A byte with
+ * bit 7 set stands for upstream's force_state (cell outside the band of its diagonal). */
+__device__ __noinline__ int ext_backtrack_warp(const uint8_t *tb, int n_col, int qlen, int tlen, int w, int i, int j, bool rev_cigar, uint32_t *cigar)
+{
+	const int lane = mmg_lane();
+	int n_cigar = 0;
+	int state = 0;
+	uint32_t cur_op = 0xf, cur_len = 0;      /* the open CIGAR run (all lanes agree; lane 0 writes) */
+	auto push = [&](uint32_t op, int len) {
+		if (op != cur_op) {
+			if (cur_len) { if (lane == 0) cigar[n_cigar] = cur_len << 4 | cur_op; ++n_cigar; }
+			cur_op = op, cur_len = 0;
+		}
+		cur_len += (uint32_t)len;
+	};
+	while (i >= 0 && j >= 0) {
+		const int r0 = i + j, i0 = i;
+		unsigned long long win = 0;
+		{
+			const int r = r0 - lane;
+			if (r >= 0) {
+				int st = 0, en = tlen - 1;
+				if (st < r - qlen + 1) st = r - qlen + 1;
+				if (en > r) en = r;
+				if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+				if (en > (r + w) >> 1) en = (r + w) >> 1;
+				st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;  /* off[r], off_end[r] */
+				const uint8_t *row = tb + (size_t)r * n_col - st;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const int ii = i0 - k;
+					unsigned long long v = 0;
+					if (ii >= 0) v = ii < st ? 0x82u : ii > en ? 0x81u : row[ii];
+					win |= v << (8 * k);
+				}
+			}
+		}
+		while (i >= 0 && j >= 0) {
+			const int dr = r0 - (i + j), di = i0 - i;
+			if (dr >= 32 || di >= 8) break;
+			const uint32_t tmp = (uint32_t)(__shfl_sync(MMG_FULL, win, dr) >> (8 * di)) & 0xff;
+			if (tmp & 0x80) state = (int)(tmp & 3);
+			else {
+				if (state == 0) state = tmp & 7;
+				else if (!(tmp >> (state + 2) & 1)) state = 0;
+				if (state == 0) state = tmp & 7;
+			}
+			if (state == 0) push(0, 1), --i, --j;
+			else if (state == 1 || state == 3) push(2, 1), --i;
+			else push(1, 1), --j;
+		}
+	}
+	if (i >= 0) push(2, i + 1);
+	if (j >= 0) push(1, j + 1);
+	push(0xf, 0);                              /* flush the open run */
+	__syncwarp();
+	if (!rev_cigar)
+		for (int k = lane; k < n_cigar >> 1; k += 32) { uint32_t t = cigar[k]; cigar[k] = cigar[n_cigar - 1 - k], cigar[n_cigar - 1 - k] = t; }
+	return n_cigar;
 }
 
 /* One pass of ksw_extd2_sse over (qlen x tlen).  All lanes of the warp call it.  SMEM = true: the job's arrays are
@@ -828,73 +903,13 @@ __device__ __noinline__ void ext_dp_pass_t(unsigned char *gbase, int T16, int Q1
 		last_st = st, last_en = en;
 	}
 	__syncwarp();
-	/* ---- backtrack (ksw_backtrack, is_rot = 1) ----
-	 * The walk is serial, and one traceback byte per step straight from global memory costs a full L2 round trip
-	 * per CIGAR base.  The warp therefore fetches a window of 32 anti-diagonals x 8 target columns below the
-	 * current cell (lane = diagonal), and every lane replays the same walk out of registers (one shuffle per
-	 * step) until it leaves the window: at least 8 and typically 16 steps per memory round trip.  A byte with
-	 * bit 7 set stands for upstream's force_state (cell outside the band of its diagonal). */
 	int n_cigar = 0;
 	{
 		int i = -1, j = -1;
-		const bool rev_cigar = (flag & EZ_REV_CIGAR) != 0;
 		if (!zdropped && !(flag & EZ_EXTZ_ONLY)) i = tlen - 1, j = qlen - 1;
 		else if (!zdropped && (flag & EZ_EXTZ_ONLY) && ez_mqe + end_bonus > ez_max) reach_end = 1, i = ez_mqe_t, j = qlen - 1;
 		else if (ez_max_t >= 0 && ez_max_q >= 0) i = ez_max_t, j = ez_max_q;
-		if (i >= 0 || j >= 0 || reach_end) {
-			int state = 0;
-			uint32_t cur_op = 0xf, cur_len = 0;      /* the open CIGAR run (all lanes agree; lane 0 writes) */
-			auto push = [&](uint32_t op, int len) {
-				if (op != cur_op) {
-					if (cur_len) { if (lane == 0) cigar[n_cigar] = cur_len << 4 | cur_op; ++n_cigar; }
-					cur_op = op, cur_len = 0;
-				}
-				cur_len += (uint32_t)len;
-			};
-			while (i >= 0 && j >= 0) {
-				const int r0 = i + j, i0 = i;
-				unsigned long long win = 0;
-				{
-					const int r = r0 - lane;
-					if (r >= 0) {
-						int st = 0, en = tlen - 1;
-						if (st < r - qlen + 1) st = r - qlen + 1;
-						if (en > r) en = r;
-						if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
-						if (en > (r + w) >> 1) en = (r + w) >> 1;
-						st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;  /* off[r], off_end[r] */
-						const uint8_t *row = tb + (size_t)r * n_col - st;
-#pragma unroll
-						for (int k = 0; k < 8; ++k) {
-							const int ii = i0 - k;
-							unsigned long long v = 0;
-							if (ii >= 0) v = ii < st ? 0x82u : ii > en ? 0x81u : row[ii];
-							win |= v << (8 * k);
-						}
-					}
-				}
-				while (i >= 0 && j >= 0) {
-					const int dr = r0 - (i + j), di = i0 - i;
-					if (dr >= 32 || di >= 8) break;
-					const uint32_t tmp = (uint32_t)(__shfl_sync(MMG_FULL, win, dr) >> (8 * di)) & 0xff;
-					if (tmp & 0x80) state = (int)(tmp & 3);
-					else {
-						if (state == 0) state = tmp & 7;
-						else if (!(tmp >> (state + 2) & 1)) state = 0;
-						if (state == 0) state = tmp & 7;
-					}
-					if (state == 0) push(0, 1), --i, --j;
-					else if (state == 1 || state == 3) push(2, 1), --i;
-					else push(1, 1), --j;
-				}
-			}
-			if (i >= 0) push(2, i + 1);
-			if (j >= 0) push(1, j + 1);
-			push(0xf, 0);                              /* flush the open run */
-			__syncwarp();
-			if (!rev_cigar)
-				for (int k = lane; k < n_cigar >> 1; k += 32) { uint32_t t = cigar[k]; cigar[k] = cigar[n_cigar - 1 - k], cigar[n_cigar - 1 - k] = t; }
-		}
+		if (i >= 0 || j >= 0 || reach_end) n_cigar = ext_backtrack_warp(tb, n_col, qlen, tlen, w, i, j, (flag & EZ_REV_CIGAR) != 0, cigar);
 	}
 	if (lane == 0) {
 		res->max = ez_max, res->max_q = ez_max_q, res->max_t = ez_max_t, res->mqe = ez_mqe, res->mqe_t = ez_mqe_t, res->score = ez_score;
@@ -997,24 +1012,41 @@ __device__ int ext_inv_score(const DpMem &m, const DevOpt &o, int qlen, int pos[
 	return gmax > 32767 ? 32767 : gmax;
 }
 
+#include "extend_fill.inc"
+
 __global__ void __launch_bounds__(EXT_DP_WARPS * 32, 4)
-ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint32_t j1, uint32_t *work)
+ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint64_t tb_slice, int last_pass, uint32_t *work)
 {
 	MMG_DYN_SMEM(smem_raw);
 	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
 	unsigned char *my_smem = smem_raw + (size_t)wib * EXT_SMEM_PER_WARP;
 	unsigned long long n_cell = 0;
+	const uint32_t j1 = ext_n_jobs(xb);
+	if (!ext_cigar_fits(xb)) return;
+	/* the traceback of a job lives only while the job runs: every resident warp owns one slice of the arena */
+	uint8_t *tb = xb.tb + (size_t)(blockIdx.x * EXT_DP_WARPS + wib) * tb_slice;
 	for (;;) {
 		uint32_t ji = j0 + mmg_next_item(work);
 		if (ji >= j1) break;
 		ExtJob *jb = &xb.jobs[ji];
+		int done = 0;                             /* finished by ext_fill_kernel or by an earlier pass with smaller slices */
+		if (lane == 0) done = jb->pad[0];         /* (lane 0 sets the mark below: the others must not re-read it) */
+		if (__shfl_sync(MMG_FULL, done, 0)) continue;
+		if (jb->tb_size > tb_slice) {             /* left to a later pass, which runs fewer warps with larger slices */
+			if (last_pass && lane == 0) {
+				atomicOr(&c.flags[jb->read], 0x10000000u), atomicOr(c.err, 0x10000000u);
+				jb->n_cigar = 0, jb->zdropped = 1, jb->max = 0, jb->max_q = jb->max_t = -1, jb->zdrop_code = 0, jb->reach_end = 0, jb->pad[0] = 1;
+			}
+			__syncwarp();
+			continue;
+		}
 		const int qlen = jb->qe - jb->qs, tlen = jb->re - jb->rs;
 		const int flag = jb->flag;
 		const uint32_t r = jb->read;
 		const char *seq = c.seq + c.off[r];
 		const int rlen = (int)(c.off[r + 1] - c.off[r]);
-		uint8_t *tb = xb.tb + jb->tb_off;
 		uint32_t *cigar = xb.jcigar + jb->cg_off;
+		if (lane == 0) jb->pad[0] = 1;
 		if (qlen <= 0 || tlen <= 0) { /* ksw_extd2_sse returns an empty ez */
 			if (lane == 0) {
 				jb->max = 0, jb->max_q = jb->max_t = jb->mqe_t = -1, jb->mqe = jb->score = KSW_NEG_INF;
@@ -1028,7 +1060,7 @@ ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint32
 		DpMem m;
 		unsigned char *base = need <= EXT_SMEM_PER_WARP ? my_smem : xb.big + (size_t)(blockIdx.x * EXT_DP_WARPS + wib) * xb.big_per_warp;
 		if (need > EXT_SMEM_PER_WARP && need > xb.big_per_warp) { /* longer than the per-warp global slice: reported by the host */
-			if (lane == 0) atomicOr(&c.flags[r], 0x20000000u), jb->n_cigar = 0, jb->zdropped = 1, jb->max = 0, jb->max_q = jb->max_t = -1, jb->zdrop_code = 0, jb->reach_end = 0;
+			if (lane == 0) atomicOr(&c.flags[r], 0x20000000u), atomicOr(c.err, 0x20000000u), jb->n_cigar = 0, jb->zdropped = 1, jb->max = 0, jb->max_q = jb->max_t = -1, jb->zdrop_code = 0, jb->reach_end = 0;
 			__syncwarp();
 			continue;
 		}

@@ -21,7 +21,7 @@ struct ExtJob {
 	int32_t qs, qe, rs, re;     /* query interval in qseq0[rev] coordinates, target interval */
 	int32_t w, zdrop, end_bonus, flag;
 	uint8_t kind, rev, zdropped, reach_end, zdrop_code, pad[3];
-	uint64_t tb_size, tb_off;   /* traceback slice (bytes) */
+	uint64_t tb_size, tb_off;   /* traceback bytes the job needs (a warp keeps them in its own slice of the arena; tb_off unused) */
 	uint32_t cg_size, n_cigar;
 	uint64_t cg_off;            /* cigar slice (u32 units) */
 	int32_t max, max_q, max_t, mqe, mqe_t, score;  /* ksw_extz_t */
@@ -43,7 +43,7 @@ struct ExtBufs {
 	ExtReg *xregs; uint64_t *xr_off; /* region slices: the same offsets as ChunkDev::regs */
 	DevReg *regs_tmp;
 	uint32_t *n_sq;             /* per read: anchors after mm_squeeze_a */
-	uint8_t *tb; uint64_t cap_tb;
+	uint8_t *tb; uint64_t cap_tb;   /* traceback arena: one slice per resident warp (a traceback lives only while its job runs) */
 	uint32_t *jcigar, *rcigar; uint64_t cap_cg;
 	unsigned long long *tb_base, *cg_base; /* [0] = base of the current round, [1] = end after the scan */
 	unsigned char *big; uint64_t big_per_warp; /* global DP arrays for jobs that do not fit shared memory */
@@ -52,11 +52,12 @@ struct ExtBufs {
 };
 
 int launch_ext_prep(const ChunkDev &c, const DevIndex &di, const DevOpt &o, const ExtBufs &xb, uint32_t r0, uint32_t r1, int round, int n_sms, cudaStream_t st, uint32_t *work);
-int launch_ext_job_scan(const ExtBufs &xb, uint32_t j0, uint32_t j1, cudaStream_t st);
-int launch_ext_dp(const ChunkDev &c, const DevIndex &di, const DevOpt &o, const ExtBufs &xb, uint32_t j0, uint32_t j1, int grid, cudaStream_t st, uint32_t *work);
+/* j1 is read from the device (*xb.n_jobs) by these two: no host round trip between prep, scan, DP and stitch */
+int launch_ext_job_scan(const ExtBufs &xb, uint32_t j0, cudaStream_t st);
+int launch_ext_dp(const ChunkDev &c, const DevIndex &di, const DevOpt &o, const ExtBufs &xb, uint32_t j0, int n_sms, cudaStream_t st, uint32_t *work);
+#define EXT_DP_COUNTERS 6   /* claim counters launch_ext_dp uses */
 int launch_ext_stitch(const ChunkDev &c, const DevIndex &di, const DevOpt &o, const ExtBufs &xb, uint32_t r0, uint32_t r1, int round, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_ext_final(const ChunkDev &c, const DevIndex &di, const DevOpt &o, const ExtBufs &xb, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_pack_cigar(const ChunkDev &c, const ExtBufs &xb, uint32_t r0, uint32_t r1, mmg_hit_t *hits, uint32_t *cigar_out, uint64_t cigar_base, uint64_t *cg_read_off, int n_sms, cudaStream_t st);
-int ext_dp_grid(int n_sms);
 
 #endif

@@ -117,6 +117,7 @@ struct mmg_aligner {
 		bool pending; uint64_t n_hits, n_cigar, hit_base, cigar_base; uint32_t read0, n_reads;
 	} rs[2];
 	unsigned long long *d_stats_pool;
+	unsigned long long *h_ctl;         /* pinned control words the compute stream copies counters into (16) */
 	uint64_t n_sub;                    /* sub-ranges issued by the current streamed call */
 };
 
@@ -220,7 +221,7 @@ static int alloc_arenas(mmg_aligner *al)
 	AL(c.cx, A); AL(c.cy, A); AL(c.u, A);
 	AL(c.n_u, R); AL(c.n_v, R); AL(c.r_off, R + 1);
 	AL(c.regs, G); AL(c.n_regs, R); AL(c.h_off, R + 1);
-	AL(c.work, 64); AL(c.flags, R); AL(c.big_list, R); AL(c.tie_list, R);
+	AL(c.work, 64); AL(c.err, 4); AL(c.flags, R); AL(c.big_list, R); AL(c.tie_list, R);
 	AL(al->d_order, R); AL(c.af_off, R + 1); AL(c.keep_bits, al->cap_keep_words); AL(c.hit_scratch, al->cap_keep_words * 32);
 	AL(al->rmq_nodes, (2 * A + 2 * R + 2) * RMQ_NODE_BYTES);
 	if (al->mo.flag & MMG_F_CIGAR) {
@@ -293,18 +294,22 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	if (idx->flag & MMG_I_HPC) { mmg_set_error("homopolymer-compressed indexes are not supported"); return MMG_EUNSUP; }
 	if (idx->offs.back() >= ((uint64_t)1 << 35)) { mmg_set_error("references of 2^35 bases or more are not supported"); return MMG_EUNSUP; }
 	CK(cudaSetDevice(device));
+#define CKA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { mmg_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); mmg_aligner_destroy(al); return MMG_ECUDA; } } while (0)
 	mmg_aligner *al = new mmg_aligner();
 	al->idx = idx, al->mo = *mo, al->device = device;
 	cudaDeviceProp prop;
-	CK(cudaGetDeviceProperties(&prop, device));
+	CKA(cudaGetDeviceProperties(&prop, device));
 	al->n_sms = prop.multiProcessorCount;
-	CK(cudaStreamCreateWithFlags(&al->stream, cudaStreamNonBlocking));
-	CK(cudaEventCreate(&al->ev0));
-	CK(cudaEventCreate(&al->ev1));
-	CK(cudaEventCreate(&al->ev_run0));
-	CK(cudaEventCreate(&al->ev_run1));
+	CKA(cudaStreamCreateWithFlags(&al->stream, cudaStreamNonBlocking));
+	CKA(cudaEventCreate(&al->ev0));
+	CKA(cudaEventCreate(&al->ev1));
+	CKA(cudaEventCreate(&al->ev_run0));
+	CKA(cudaEventCreate(&al->ev_run1));
 	al->last_run_ms = 0;
 	al->pool = new HostPool();
+	al->h_ctl = 0;
+	CKA(cudaMallocHost((void**)&al->h_ctl, 16 * sizeof(unsigned long long)));
+	memset(al->h_ctl, 0, 16 * sizeof(unsigned long long));
 	al->ev_used = 0, al->s_in = 0, al->s_out = 0, al->stream_ready = false, al->d_stats_pool = 0, al->n_sub = 0;
 	memset(al->in_bases, 0, sizeof(al->in_bases)), memset(al->in_off, 0, sizeof(al->in_off)), memset(al->h_in_off, 0, sizeof(al->h_in_off));
 	memset(al->ev_in, 0, sizeof(al->ev_in)), memset(al->ev_free, 0, sizeof(al->ev_free)), memset(al->rs, 0, sizeof(al->rs));
@@ -321,9 +326,9 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	}
 	al->anchor_filter = 1;
 	al->dual_stream = 0, al->dual_min = 4096; /* measured: 118.2 vs 119.7 ms per step on configs[2] - kept as an option, off by default */
-	CK(cudaStreamCreateWithFlags(&al->st2, cudaStreamNonBlocking));
-	CK(cudaEventCreateWithFlags(&al->ev_fork, cudaEventDisableTiming));
-	CK(cudaEventCreateWithFlags(&al->ev_join, cudaEventDisableTiming));
+	CKA(cudaStreamCreateWithFlags(&al->st2, cudaStreamNonBlocking));
+	CKA(cudaEventCreateWithFlags(&al->ev_fork, cudaEventDisableTiming));
+	CKA(cudaEventCreateWithFlags(&al->ev_join, cudaEventDisableTiming));
 	al->ramp_shift = 1;
 	al->cap_tb = (uint64_t)32 << 30, al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48, al->big_per_warp = (uint64_t)1 << 20;
 	memset(&al->xb, 0, sizeof(al->xb));
@@ -374,6 +379,7 @@ void mmg_aligner_destroy(mmg_aligner *al)
 		}
 		if (del) delete al->pool;
 	}
+	if (al->h_ctl) cudaFreeHost(al->h_ctl);
 	if (al->ev0) cudaEventDestroy(al->ev0);
 	if (al->ev1) cudaEventDestroy(al->ev1);
 	if (al->ev_run0) cudaEventDestroy(al->ev_run0);
@@ -479,75 +485,50 @@ static void stage_collect(mmg_aligner *al)
 #define STAGE_END(id) do { al->stage_launches[id] += 1; if (al->profile) cudaEventRecord(stage_event(al, id), st); } while (0)
 
 /* Base-level alignment of the regions of reads [s0, s1): rounds of prep -> DP jobs -> stitch until no
- * region is left pending (a z-drop split creates a region that is aligned in the next round). */
+ * region is left pending (a z-drop split creates a region that is aligned in the next round).  Within a round the
+ * kernels read the job count from device memory, so the host synchronises once per round (to learn whether another
+ * round is needed and whether an arena overflowed), not between the kernels. */
 static int run_extension(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t s0, uint32_t s1, uint32_t *work, int *wi_, uint64_t *n_cg_sub)
 {
 	cudaStream_t st = al->stream;
 	ExtBufs &xb = al->xb;
 	int wi = *wi_;
 	uint32_t n_jobs_prev = 0;
-	unsigned long long bases[2] = {0, 0}, cg_end = 0;
+	unsigned long long cg_end = 0;
 	CK(cudaMemsetAsync(xb.n_jobs, 0, 4, st));
-	for (int round = 0; round < 64; ++round) {
-		if (wi + 6 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
+	int round = 0;
+	for (; round < 64; ++round) {
+		if (wi + EXT_DP_COUNTERS + 3 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
 		STAGE_BEGIN();
 		launch_ext_prep(c, al->di, al->dopt, xb, s0, s1, round, al->n_sms, st, work + wi++);
-		uint32_t n_jobs = 0;
-		CK(cudaMemcpyAsync(&n_jobs, xb.n_jobs, 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		if (n_jobs > xb.cap_jobs) { mmg_set_error("extension job arena overflow (%u jobs)", n_jobs); return MMG_ENOMEM; }
-		bases[0] = 0, bases[1] = 0;
-		CK(cudaMemcpyAsync(xb.tb_base, bases, 8, cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(xb.cg_base, &cg_end, 8, cudaMemcpyHostToDevice, st));
-		launch_ext_job_scan(xb, n_jobs_prev, n_jobs, st);
-		unsigned long long tb_end = 0;
-		CK(cudaMemcpyAsync(&tb_end, xb.tb_base + 1, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(&cg_end, xb.cg_base + 1, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		STAGE_END(ST_EXTEND);
-		if (cg_end > xb.cap_cg) { mmg_set_error("extension CIGAR arena overflow (%llu > cigar_cap)", cg_end); return MMG_ENOMEM; }
-		/* traceback arena: jobs run in waves that fit cap_tb */
-		std::vector<uint64_t> tboff;
-		if (tb_end > xb.cap_tb) {
-			std::vector<ExtJob> hj(n_jobs - n_jobs_prev);
-			CK(cudaMemcpy(hj.data(), xb.jobs + n_jobs_prev, hj.size() * sizeof(ExtJob), cudaMemcpyDeviceToHost));
-			for (size_t i = 0; i < hj.size(); ++i) {
-				if (hj[i].tb_size > xb.cap_tb) { mmg_set_error("one alignment needs a %llu-byte traceback (> tb_cap)", (unsigned long long)hj[i].tb_size); return MMG_ENOMEM; }
-				tboff.push_back(hj[i].tb_off);
-			}
-		}
-		for (uint32_t j0 = n_jobs_prev; j0 < n_jobs;) {
-			uint32_t j1 = n_jobs;
-			uint64_t wave_base = 0;
-			if (!tboff.empty()) {
-				wave_base = tboff[j0 - n_jobs_prev];
-				j1 = j0;
-				while (j1 < n_jobs && (j1 + 1 < n_jobs ? tboff[j1 + 1 - n_jobs_prev] : tb_end) - wave_base <= xb.cap_tb) ++j1;
-			}
-			ExtBufs xw = xb;
-			xw.tb = xb.tb - wave_base;
-			if (wi + 4 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
-			STAGE_BEGIN();
-			launch_ext_dp(c, al->di, al->dopt, xw, j0, j1, ext_dp_grid(al->n_sms), st, work + wi++);
-			STAGE_END(ST_EXTEND);
-			j0 = j1;
-		}
-		STAGE_BEGIN();
+		al->h_ctl[0] = cg_end;   /* pinned: the CIGAR slices of this round's jobs start where the last round ended */
+		CK(cudaMemcpyAsync(xb.cg_base, al->h_ctl, 8, cudaMemcpyHostToDevice, st));
+		launch_ext_job_scan(xb, n_jobs_prev, st);
+		launch_ext_dp(c, al->di, al->dopt, xb, n_jobs_prev, al->n_sms, st, work + wi); wi += EXT_DP_COUNTERS;
 		CK(cudaMemsetAsync(xb.n_pending, 0, 4, st));
 		launch_ext_stitch(c, al->di, al->dopt, xb, s0, s1, round, al->n_sms, st, work + wi++);
-		uint32_t n_pending = 0;
-		CK(cudaMemcpyAsync(&n_pending, xb.n_pending, 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		CK(cudaMemcpyAsync(al->h_ctl + 1, xb.cg_base + 1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(al->h_ctl + 2, xb.n_jobs, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(al->h_ctl + 3, xb.n_pending, 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(al->h_ctl + 4, c.err, 4, cudaMemcpyDeviceToHost, st));
 		STAGE_END(ST_EXTEND);
+		CK(cudaStreamSynchronize(st));
+		cg_end = al->h_ctl[1];
+		const uint32_t n_jobs = (uint32_t)al->h_ctl[2], n_pending = (uint32_t)al->h_ctl[3], err = (uint32_t)al->h_ctl[4];
+		if (n_jobs > xb.cap_jobs || (err & 0x40000000u)) { mmg_set_error("extension job arena overflow (%u jobs > jobs_cap)", n_jobs); return MMG_ENOMEM; }
+		if (cg_end > xb.cap_cg) { mmg_set_error("extension CIGAR arena overflow (%llu > cigar_cap)", cg_end); return MMG_ENOMEM; }
+		if (err & 0x10000000u) { mmg_set_error("one alignment needs more traceback memory than tb_cap / 4 (%llu bytes)", (unsigned long long)(xb.cap_tb / 4)); return MMG_ENOMEM; }
+		if (err & 0x20000000u) { mmg_set_error("one alignment is longer than the per-warp DP slice (big_per_warp)"); return MMG_ENOMEM; }
 		n_jobs_prev = n_jobs;
 		if (n_pending == 0) break;
 	}
+	if (round == 64) { mmg_set_error("internal: regions still pending after 64 alignment rounds"); return MMG_ECUDA; }
 	STAGE_BEGIN();
 	launch_ext_final(c, al->di, al->dopt, xb, s0, s1, al->n_sms, st, work + wi++);
 	launch_scan_u32(xb.n_sq + s0, al->cg_read_off + s0, s1 - s0, st);
-	CK(cudaMemcpyAsync(n_cg_sub, al->cg_read_off + s1, 8, cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
 	STAGE_END(ST_EXTEND);
+	CK(cudaMemcpyAsync(al->h_ctl + 5, al->cg_read_off + s1, 8, cudaMemcpyDeviceToHost, st)); /* read by run_chunk after its final synchronisation */
+	(void)n_cg_sub;
 	*wi_ = wi;
 	return MMG_OK;
 }
@@ -617,6 +598,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	uint32_t *work = c.work;
 	int wi = 0;
 	CK(cudaMemsetAsync(c.work, 0, 64 * 4, st));
+	CK(cudaMemsetAsync(c.err, 0, 4, st));
 	CK(cudaMemsetAsync(c.flags, 0, (size_t)c.n_reads * 4, st));
 	/* work order: reads by descending length, so that a kernel's persistent warps take the long reads first and the
 	 * launch does not end with a few of them still running (computed on the device: a host-side table would have to
@@ -706,10 +688,14 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 		STAGE_BEGIN();
 		launch_scan_u32(c.n_regs + s0, c.h_off + s0, s1 - s0, st);
 		STAGE_END(ST_SCAN);
-		uint64_t n_hits_sub = 0, n_regs_sub = 0;
-		CK(cudaMemcpyAsync(&n_hits_sub, c.h_off + s1, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(&n_regs_sub, c.r_off + s1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(al->h_ctl + 6, c.h_off + s1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(al->h_ctl + 7, c.r_off + s1, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(al->h_ctl + 8, c.err, 4, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
+		const uint64_t n_hits_sub = al->h_ctl[6], n_regs_sub = al->h_ctl[7];
+		if (with_cigar) n_cg_sub = al->h_ctl[5];
+		if ((uint32_t)al->h_ctl[8] & 0x80000000u) { mmg_set_error("region arena overflow (regs_cap)"); return MMG_ENOMEM; }
+		if ((uint32_t)al->h_ctl[8]) { mmg_set_error("device arena overflow (flags 0x%x)", (unsigned)al->h_ctl[8]); return MMG_ENOMEM; }
 		if (n_regs_sub > al->cap_regs) { mmg_set_error("region arena overflow (%llu > regs_cap)", (unsigned long long)n_regs_sub); return MMG_ENOMEM; }
 		if (!b->streamed) {
 			if (b->n_hits_dev + n_hits_sub > b->hits_cap) { mmg_set_error("result pool overflow (%llu hits)", (unsigned long long)(b->n_hits_dev + n_hits_sub)); return MMG_ENOMEM; }

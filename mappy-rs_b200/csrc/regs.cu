@@ -61,7 +61,7 @@ regs_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint64_
 			}
 			n_regs = __shfl_sync(MMG_FULL, n_regs, 0);
 		} else if (n_u > 0) {
-			if (lane == 0) atomicOr(&c.flags[r], 0x80000000u); /* region arena overflow: reported by the host */
+			if (lane == 0) atomicOr(&c.flags[r], 0x80000000u), atomicOr(c.err, 0x80000000u); /* region arena overflow: reported by the host */
 		}
 		if (lane == 0) c.n_regs[r] = (uint32_t)n_regs;
 		tot_kept += c.n_v[r], tot_regs += n_regs;
@@ -69,7 +69,7 @@ regs_kernel(ChunkDev c, DevIndex di, DevOpt o, uint32_t r0, uint32_t r1, uint64_
 	}
 	if (lane == 0 && (tot_kept | tot_regs)) {
 		atomicAdd(&c.stats[6], tot_kept);
-		atomicAdd(&c.stats[8], tot_regs);
+		if (!(o.flag & MMG_F_CIGAR)) atomicAdd(&c.stats[8], tot_regs); /* with CIGAR the final count is taken after alignment (ext_final_kernel) */
 	}
 }
 

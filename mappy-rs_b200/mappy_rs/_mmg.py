@@ -51,7 +51,7 @@ HIT_DTYPE = np.dtype([
     ("n_cigar", "<u4"), ("cigar_off", "<u8"),
 ], align=True)
 
-STAT_NAMES = ["n_bases", "n_mz", "n_seed", "n_hit", "n_anchor", "n_iter", "n_kept", "n_cell", "n_regs", "n_rechain", "n_dropped"]
+STAT_NAMES = ["n_bases", "n_mz", "n_seed", "n_hit", "n_anchor", "n_iter", "n_kept", "n_cell", "n_regs", "n_rechain", "n_dropped", "n_cell_fill"]
 N_STAGES = 12
 
 EXPORTS = ["mmg_host_alloc", "mmg_host_free", "mmg_set_opt", "mmg_mapopt_update", "mmg_index_open", "mmg_index_build", "mmg_index_build_on", "mmg_debug_int32_peak", "mmg_index_dump", "mmg_index_destroy",

@@ -11,6 +11,7 @@
  * src/lib.rs:1094-1106); everything else here is parity unpinned.
  */
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <assert.h>
 #include <string>
@@ -255,6 +256,7 @@ static void mm_align_pair(const mm_mapopt_t *opt, int qlen, const uint8_t *qseq,
 {
 	if (opt->transition != 0 && opt->b != opt->transition)
 		flag |= KSW_EZ_GENERIC_SC;
+	{ static FILE *jl = getenv("MM2O_JOBLOG") ? fopen(getenv("MM2O_JOBLOG"), "w") : 0; if (jl) fprintf(jl, "%d %d %d %d\n", qlen, tlen, w, flag); }
 	if (opt->max_sw_mat > 0 && (int64_t)tlen * qlen > opt->max_sw_mat) {
 		ksw_reset_extz(ez);
 		ez->zdropped = 1;
