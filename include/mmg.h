@@ -157,6 +157,11 @@ uint64_t mmg_index_entries(const mmg_index *idx, uint64_t *minier, uint64_t *pos
  * replaces the minimap2::Aligner value + per-thread mm_tbuf_t (src/lib.rs:419-425,
  * 545): uploads the index to `device` once; it stays GPU-resident. */
 int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device, mmg_aligner **out);
+/* the same across several GPUs of one box (what `enable_threading(n)` + N workers on one shared index are in the
+ * reference, src/lib.rs:541-553): the index is uploaded / built once and replicated to the other devices with peer
+ * copies, every mmg_map_batch on the returned aligner shards its reads by bases over the devices (one host thread and
+ * one set of streams per device, no collective) and gathers the results in read order. */
+int mmg_aligner_create_multi(const mmg_index *idx, const mmg_mapopt_t *mo, const int *devices, int n_dev, mmg_aligner **out);
 void mmg_aligner_destroy(mmg_aligner *al);
 /* tuning knobs of the device pipeline (not mapping semantics):
  * "chunk_bases", "chunk_reads", "anchor_cap", "profile" (1 = per-stage CUDA events) */

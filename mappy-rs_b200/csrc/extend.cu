@@ -1015,7 +1015,7 @@ __device__ int ext_inv_score(const DpMem &m, const DevOpt &o, int qlen, int pos[
 #include "extend_fill.inc"
 
 __global__ void __launch_bounds__(EXT_DP_WARPS * 32, 4)
-ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint64_t tb_slice, int last_pass, uint32_t *work)
+ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint64_t tb_slice, int pass, int last_pass, uint32_t *work)
 {
 	MMG_DYN_SMEM(smem_raw);
 	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
@@ -1025,17 +1025,38 @@ ext_dp_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t j0, uint64
 	if (!ext_cigar_fits(xb)) return;
 	/* the traceback of a job lives only while the job runs: every resident warp owns one slice of the arena */
 	uint8_t *tb = xb.tb + (size_t)(blockIdx.x * EXT_DP_WARPS + wib) * tb_slice;
+	/* pass 0 walks the jobs of this round, 32 per claim, skipping the ones ext_fill_kernel finished; a job whose
+	 * traceback does not fit this pass' slice goes on a list for the next pass (fewer warps, larger slices) */
+	uint32_t seg0 = 0, n_list = 0;
+	for (int k = 0; k + 1 < pass; ++k) seg0 += xb.ovf_n[k];
+	if (pass > 0) n_list = xb.ovf_n[pass - 1];
+	const uint32_t seg1 = pass > 0 ? seg0 + n_list : 0;
+	uint32_t todo = 0, base = 0;
 	for (;;) {
-		uint32_t ji = j0 + mmg_next_item(work);
-		if (ji >= j1) break;
+		uint32_t ji;
+		if (pass == 0) {
+			while (!todo) {
+				base = j0 + 32u * mmg_next_item(work);
+				if (base >= j1) break;
+				const uint32_t jl = base + (uint32_t)lane;
+				todo = __ballot_sync(MMG_FULL, jl < j1 && !xb.jobs[jl].pad[0]);
+			}
+			if (!todo) break;
+			ji = base + (uint32_t)(__ffs((int)todo) - 1);
+			todo &= todo - 1;
+		} else {
+			const uint32_t k = mmg_next_item(work);
+			if (k >= n_list) break;
+			ji = xb.ovf[seg0 + k];
+		}
 		ExtJob *jb = &xb.jobs[ji];
-		int done = 0;                             /* finished by ext_fill_kernel or by an earlier pass with smaller slices */
-		if (lane == 0) done = jb->pad[0];         /* (lane 0 sets the mark below: the others must not re-read it) */
-		if (__shfl_sync(MMG_FULL, done, 0)) continue;
-		if (jb->tb_size > tb_slice) {             /* left to a later pass, which runs fewer warps with larger slices */
-			if (last_pass && lane == 0) {
-				atomicOr(&c.flags[jb->read], 0x10000000u), atomicOr(c.err, 0x10000000u);
-				jb->n_cigar = 0, jb->zdropped = 1, jb->max = 0, jb->max_q = jb->max_t = -1, jb->zdrop_code = 0, jb->reach_end = 0, jb->pad[0] = 1;
+		if (jb->tb_size > tb_slice) {
+			if (lane == 0) {
+				if (!last_pass) xb.ovf[seg1 + atomicAdd(&xb.ovf_n[pass], 1u)] = ji;
+				else {
+					atomicOr(&c.flags[jb->read], 0x10000000u), atomicOr(c.err, 0x10000000u);
+					jb->n_cigar = 0, jb->zdropped = 1, jb->max = 0, jb->max_q = jb->max_t = -1, jb->zdrop_code = 0, jb->reach_end = 0, jb->pad[0] = 1;
+				}
 			}
 			__syncwarp();
 			continue;

@@ -48,6 +48,7 @@ struct ExtBufs {
 	unsigned long long *tb_base, *cg_base; /* [0] = base of the current round, [1] = end after the scan */
 	unsigned char *big; uint64_t big_per_warp; /* global DP arrays for jobs that do not fit shared memory */
 	uint32_t *n_pending;        /* regions created by splits, to be aligned in the next round */
+	uint32_t *ovf, *ovf_n;      /* jobs whose traceback did not fit the slice of a DP pass, one list segment per pass; ovf_n[4] */
 	uint32_t *reg_cap;          /* per read: capacity of its region slice */
 };
 

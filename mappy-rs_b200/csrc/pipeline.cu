@@ -14,6 +14,8 @@
 #include <vector>
 #include <algorithm>
 #include <mutex>
+#include <thread>
+#include <string>
 #include "mmg_internal.h"
 #include "dev_common.cuh"
 #include "stages.h"
@@ -69,6 +71,9 @@ static void pool_release(HostPool *hp, void *p, uint64_t bytes)
 }
 
 struct mmg_aligner {
+	/* A multi-device aligner (mmg_aligner_create_multi) is a group: one full single-device aligner per GPU in `subs`,
+	 * the index replicated on each; mmg_map_batch on the group shards the reads by bases and gathers in read order. */
+	std::vector<mmg_aligner*> subs;
 	HostPool *pool;
 	const mmg_index *idx;
 	mmg_mapopt_t mo;
@@ -156,13 +161,36 @@ template<typename T> static int dev_alloc(mmg_aligner *al, T **p, uint64_t n)
 	return MMG_OK;
 }
 
-static int upload_index(mmg_aligner *al)
+/* `src`: a device copy of the same index on GPU `src_dev` (another aligner's, or the device the index was built on):
+ * replicated over NVLink with peer copies instead of a second trip through the host */
+static int upload_index(mmg_aligner *al, const DevIndex *src = 0, int src_dev = -1)
 {
 	const mmg_index *idx = al->idx;
 	DevIndex &di = al->di;
 	di.k = idx->k, di.w = idx->w, di.b = idx->b, di.flag = idx->flag, di.n_seq = idx->n_seq, di.hbits = idx->hbits;
 	if (idx->dev_device == al->device && idx->dev_htab) { /* built on this device (index_dev.cu): used in place */
 		di.htab = (const mmg_u128*)idx->dev_htab, di.pos = idx->dev_pos, di.S = idx->dev_S, di.seq_off = idx->dev_seq_off, di.seq_len = idx->dev_seq_len;
+		return MMG_OK;
+	}
+	DevIndex from;
+	if (!src && idx->dev_htab && idx->dev_device >= 0) {
+		from.htab = (const mmg_u128*)idx->dev_htab, from.pos = idx->dev_pos, from.S = idx->dev_S, from.seq_off = idx->dev_seq_off, from.seq_len = idx->dev_seq_len;
+		src = &from, src_dev = idx->dev_device;
+	}
+	if (src && src_dev >= 0 && src_dev != al->device) {
+		const size_t nslots = (size_t)1 << idx->hbits, n_pos = idx->dev_htab ? (size_t)idx->n_pos : idx->pos.size(), n_S = idx->S.size();
+		mmg_u128 *d_tab; uint64_t *d_pos, *d_soff; uint32_t *d_S, *d_slen;
+		int rc;
+		if ((rc = dev_alloc(al, &d_tab, nslots)) || (rc = dev_alloc(al, &d_pos, n_pos)) || (rc = dev_alloc(al, &d_S, n_S)) ||
+		    (rc = dev_alloc(al, &d_soff, idx->offs.size())) || (rc = dev_alloc(al, &d_slen, idx->lens.size()))) return rc;
+		int can = 0;
+		if (cudaDeviceCanAccessPeer(&can, al->device, src_dev) == cudaSuccess && can) { cudaDeviceEnablePeerAccess(src_dev, 0); cudaGetLastError(); }
+		CK(cudaMemcpyPeer(d_tab, al->device, src->htab, src_dev, nslots * sizeof(mmg_u128)));
+		if (n_pos) CK(cudaMemcpyPeer(d_pos, al->device, src->pos, src_dev, n_pos * 8));
+		if (n_S) CK(cudaMemcpyPeer(d_S, al->device, src->S, src_dev, n_S * 4));
+		CK(cudaMemcpy(d_soff, idx->offs.data(), idx->offs.size() * 8, cudaMemcpyHostToDevice));
+		if (!idx->lens.empty()) CK(cudaMemcpy(d_slen, idx->lens.data(), idx->lens.size() * 4, cudaMemcpyHostToDevice));
+		di.htab = d_tab, di.pos = d_pos, di.S = d_S, di.seq_off = d_soff, di.seq_len = d_slen;
 		return MMG_OK;
 	}
 	{ int rc0 = mmg_index_ensure_host(const_cast<mmg_index*>(idx)); if (rc0) return rc0; }
@@ -229,7 +257,7 @@ static int alloc_arenas(mmg_aligner *al)
 		x.cap_jobs = al->cap_jobs, x.cap_tb = al->cap_tb, x.cap_cg = al->cap_cg, x.big_per_warp = al->big_per_warp;
 		AL(x.jobs, x.cap_jobs); AL(x.n_jobs, 4); AL(x.xregs, G); AL(x.regs_tmp, G); AL(x.n_sq, R);
 		AL(x.tb, x.cap_tb + 64); AL(x.jcigar, x.cap_cg); AL(x.rcigar, x.cap_cg);
-		AL(x.tb_base, 2); AL(x.cg_base, 2); AL(x.n_pending, 4); AL(x.reg_cap, R);
+		AL(x.tb_base, 2); AL(x.cg_base, 2); AL(x.n_pending, 4); AL(x.reg_cap, R); AL(x.ovf, x.cap_jobs); AL(x.ovf_n, 4);
 		AL(x.big, (uint64_t)al->n_sms * 32 * x.big_per_warp); /* one slice per resident warp of the prep (8x4 per SM) and DP (4x4 per SM) grids */
 		AL(al->cg_read_off, R + 1);
 		x.xr_off = c.r_off;
@@ -277,9 +305,7 @@ __global__ void reg_cap_kernel(const uint32_t *n_u, uint32_t *cap, uint32_t n)
 	if (i < n) cap[i] = n_u[i] ? 2 * n_u[i] + 4 : 0;
 }
 
-extern "C" {
-
-int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device, mmg_aligner **out)
+static int aligner_create_on(const mmg_index *idx, const mmg_mapopt_t *mo, int device, const DevIndex *src, int src_dev, mmg_aligner **out)
 {
 	*out = 0;
 	int n_dev = 0;
@@ -336,16 +362,50 @@ int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device,
 	memset(al->stage_ms, 0, sizeof(al->stage_ms));
 	memset(al->stage_launches, 0, sizeof(al->stage_launches));
 	memset(&al->cd, 0, sizeof(al->cd));
-	int rc = upload_index(al);
+	int rc = upload_index(al, src, src_dev);
 	if (rc) { mmg_aligner_destroy(al); return rc; }
 	fill_devopt(al);
 	*out = al;
 	return MMG_OK;
 }
 
+extern "C" {
+
+int mmg_aligner_create(const mmg_index *idx, const mmg_mapopt_t *mo, int device, mmg_aligner **out)
+{
+	return aligner_create_on(idx, mo, device, 0, -1, out);
+}
+
+int mmg_aligner_create_multi(const mmg_index *idx, const mmg_mapopt_t *mo, const int *devices, int n_dev, mmg_aligner **out)
+{
+	*out = 0;
+	if (n_dev < 1 || !devices) { mmg_set_error("mmg_aligner_create_multi needs at least one device"); return MMG_EINVAL; }
+	for (int a = 0; a < n_dev; ++a)
+		for (int b = 0; b < a; ++b)
+			if (devices[a] == devices[b]) { mmg_set_error("device %d is listed twice", devices[a]); return MMG_EINVAL; }
+	mmg_aligner *g = new mmg_aligner();
+	g->idx = idx, g->mo = *mo, g->device = devices[0];
+	/* the first member uploads the index (or uses it in place where it was built); the others copy it from a peer */
+	int first = 0;
+	for (int a = 0; a < n_dev; ++a) if (devices[a] == idx->dev_device) first = a;
+	g->subs.assign(n_dev, (mmg_aligner*)0);
+	int rc = aligner_create_on(idx, mo, devices[first], 0, -1, &g->subs[first]);
+	for (int a = 0; a < n_dev && !rc; ++a)
+		if (a != first) rc = aligner_create_on(idx, mo, devices[a], &g->subs[first]->di, devices[first], &g->subs[a]);
+	if (rc) { mmg_aligner_destroy(g); return rc; }
+	*out = g;
+	return MMG_OK;
+}
+
 void mmg_aligner_destroy(mmg_aligner *al)
 {
 	if (!al) return;
+	if (!al->subs.empty()) {
+		for (size_t a = 0; a < al->subs.size(); ++a) mmg_aligner_destroy(al->subs[a]);
+		delete al;
+		return;
+	}
+	cudaSetDevice(al->device);
 	for (size_t i = 0; i < al->dev_allocs.size(); ++i) cudaFree(al->dev_allocs[i]);
 	if (al->stream) cudaStreamDestroy(al->stream);
 	if (al->st2) cudaStreamDestroy(al->st2);
@@ -398,6 +458,10 @@ void mmg_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 {
+	if (!al->subs.empty()) {
+		for (size_t a = 0; a < al->subs.size(); ++a) { int rc = mmg_aligner_set(al->subs[a], key, v); if (rc) return rc; }
+		return MMG_OK;
+	}
 	if (strcmp(key, "profile") == 0) { al->profile = (int)v; return MMG_OK; }
 	if (strcmp(key, "sort_small_max") == 0) { mmg_sort_set_small_max((int)v); return MMG_OK; }
 	if (strcmp(key, "anchor_filter") == 0) { al->anchor_filter = v != 0; return MMG_OK; }
@@ -420,6 +484,7 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets, uint32_t n_reads, mmg_batch **out)
 {
 	*out = 0;
+	if (!al->subs.empty()) { mmg_set_error("upload / run / fetch time one device: use mmg_map_batch on a multi-device aligner"); return MMG_EUNSUP; }
 	CK(cudaSetDevice(al->device));
 	mmg_batch *b = new mmg_batch();
 	b->n_reads = n_reads, b->h_bases = bases, b->h_off = offsets;
@@ -504,6 +569,7 @@ static int run_extension(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t s0
 		al->h_ctl[0] = cg_end;   /* pinned: the CIGAR slices of this round's jobs start where the last round ended */
 		CK(cudaMemcpyAsync(xb.cg_base, al->h_ctl, 8, cudaMemcpyHostToDevice, st));
 		launch_ext_job_scan(xb, n_jobs_prev, st);
+		CK(cudaMemsetAsync(xb.ovf_n, 0, 16, st));
 		launch_ext_dp(c, al->di, al->dopt, xb, n_jobs_prev, al->n_sms, st, work + wi); wi += EXT_DP_COUNTERS;
 		CK(cudaMemsetAsync(xb.n_pending, 0, 4, st));
 		launch_ext_stitch(c, al->di, al->dopt, xb, s0, s1, round, al->n_sms, st, work + wi++);
@@ -796,6 +862,7 @@ extern "C" {
 
 int mmg_batch_run(mmg_aligner *al, mmg_batch *b)
 {
+	if (!al->subs.empty()) { mmg_set_error("upload / run / fetch time one device: use mmg_map_batch on a multi-device aligner"); return MMG_EUNSUP; }
 	if (!b->uploaded) { mmg_set_error("batch not uploaded"); return MMG_EINVAL; }
 	CK(cudaSetDevice(al->device));
 	int rc = alloc_arenas(al);
@@ -831,6 +898,7 @@ int mmg_batch_fetch(mmg_aligner *al, mmg_batch *b)
 {
 	if (!b->ran) { mmg_set_error("batch not run"); return MMG_EINVAL; }
 	if (b->streamed) { b->fetched = true; return MMG_OK; }
+	if (!al->subs.empty()) { mmg_set_error("upload / run / fetch time one device: use mmg_map_batch on a multi-device aligner"); return MMG_EUNSUP; }
 	CK(cudaSetDevice(al->device));
 	cudaStream_t st = al->stream;
 	std::vector<uint32_t> nregs(b->n_reads + 1);
@@ -919,9 +987,86 @@ static int map_batch_streamed(mmg_aligner *al, mmg_batch *b)
 	return MMG_OK;
 }
 
+/* Multi-device mmg_map_batch: the reads are cut into contiguous shards of (nearly) equal BASES, one per device; every
+ * device maps its shard with its own streams on its own host thread (no collective: the path has no exchange step),
+ * and the results are gathered into one batch in read order - what N workers sharing one index do in the reference
+ * (/root/reference/src/lib.rs:545-553). */
+static int map_batch_group(mmg_aligner *g, const char *bases, const uint64_t *offsets, uint32_t n_reads, mmg_batch **out)
+{
+	const size_t nd = g->subs.size();
+	std::vector<uint32_t> cut(nd + 1, 0);
+	const uint64_t total = n_reads ? offsets[n_reads] - offsets[0] : 0;
+	for (size_t d = 1; d < nd; ++d) { /* first read whose start offset reaches the d-th share of the bases */
+		const uint64_t target = offsets[0] + total / nd * d + total % nd * d / nd;
+		uint32_t i = (uint32_t)(std::lower_bound(offsets, offsets + n_reads + 1, target) - offsets);
+		cut[d] = i < cut[d - 1] ? cut[d - 1] : i > n_reads ? n_reads : i;
+	}
+	cut[nd] = n_reads;
+	std::vector<mmg_batch*> sb(nd, (mmg_batch*)0);
+	std::vector<int> rcs(nd, 0);
+	std::vector<std::string> errs(nd);
+	std::vector<std::thread> th;
+	for (size_t d = 0; d < nd; ++d)
+		th.emplace_back([&, d]() {
+			rcs[d] = mmg_map_batch(g->subs[d], bases, offsets + cut[d], cut[d + 1] - cut[d], &sb[d]);
+			if (rcs[d]) errs[d] = mmg_last_error();
+		});
+	for (size_t d = 0; d < nd; ++d) th[d].join();
+	for (size_t d = 0; d < nd; ++d)
+		if (rcs[d]) {
+			mmg_set_error("device %d: %s", g->subs[d]->device, errs[d].c_str());
+			for (size_t k = 0; k < nd; ++k) mmg_batch_destroy(sb[k]);
+			return rcs[d];
+		}
+	mmg_batch *b = new mmg_batch();
+	b->n_reads = n_reads, b->n_bases = total, b->h_bases = bases, b->h_off = offsets;
+	b->d_bases = 0, b->d_off = 0, b->d_hits = 0, b->d_nregs = 0, b->d_stats = 0, b->d_cigar = 0, b->cigar_cap = 0, b->hits_cap = 0;
+	b->uploaded = false, b->ran = b->fetched = true, b->streamed = true;
+	b->pool = g->subs[0]->pool, b->ph = 0, b->ph_bytes = 0, b->pc = 0, b->pc_bytes = 0, b->dbg_r0 = b->dbg_r1 = 0;
+	memset(b->stats, 0, sizeof(b->stats));
+	std::vector<uint64_t> hbase(nd + 1, 0), cbase(nd + 1, 0);
+	for (size_t d = 0; d < nd; ++d) hbase[d + 1] = hbase[d] + sb[d]->n_hits_dev, cbase[d + 1] = cbase[d] + sb[d]->n_cigar_dev;
+	b->n_hits_dev = hbase[nd], b->n_cigar_dev = cbase[nd];
+	b->ph = (mmg_hit_t*)pool_acquire(b->pool, (b->n_hits_dev + 1) * sizeof(mmg_hit_t), &b->ph_bytes);
+	if (b->n_cigar_dev) b->pc = (uint32_t*)pool_acquire(b->pool, b->n_cigar_dev * 4, &b->pc_bytes);
+	if (!b->ph || (b->n_cigar_dev && !b->pc)) {
+		mmg_set_error("cannot allocate host memory for the gathered results");
+		for (size_t k = 0; k < nd; ++k) mmg_batch_destroy(sb[k]);
+		mmg_batch_destroy(b);
+		return MMG_ENOMEM;
+	}
+	b->hit_off.resize((size_t)n_reads + 1);
+	th.clear();
+	for (size_t d = 0; d < nd; ++d)
+		th.emplace_back([&, d]() { /* gather: every shard moves its own records; CIGAR offsets are rebased */
+			const mmg_batch *s = sb[d];
+			for (uint32_t i = 0; i < s->n_reads; ++i) b->hit_off[cut[d] + i] = hbase[d] + s->hit_off[i];
+			mmg_hit_t *dst = b->ph + hbase[d];
+			if (s->n_hits_dev) memcpy(dst, s->ph, s->n_hits_dev * sizeof(mmg_hit_t));
+			if (cbase[d]) for (uint64_t i = 0; i < s->n_hits_dev; ++i) dst[i].cigar_off += cbase[d];
+			if (s->n_cigar_dev) memcpy(b->pc + cbase[d], s->pc, s->n_cigar_dev * 4);
+		});
+	for (size_t d = 0; d < nd; ++d) th[d].join();
+	b->hit_off[n_reads] = b->n_hits_dev;
+	g->last_run_ms = 0;
+	memset(g->stage_ms, 0, sizeof(g->stage_ms)), memset(g->stage_launches, 0, sizeof(g->stage_launches));
+	for (size_t d = 0; d < nd; ++d) {
+		for (int k = 0; k < MMG_N_STATS; ++k) b->stats[k] += sb[d]->stats[k];
+		if (g->subs[d]->last_run_ms > g->last_run_ms) g->last_run_ms = g->subs[d]->last_run_ms;   /* devices run side by side */
+		for (int k = 0; k < MMG_N_STAGES; ++k) {
+			if (g->subs[d]->stage_ms[k] > g->stage_ms[k]) g->stage_ms[k] = g->subs[d]->stage_ms[k];
+			g->stage_launches[k] += g->subs[d]->stage_launches[k];
+		}
+		mmg_batch_destroy(sb[d]);
+	}
+	*out = b;
+	return MMG_OK;
+}
+
 int mmg_map_batch(mmg_aligner *al, const char *bases, const uint64_t *offsets, uint32_t n_reads, mmg_batch **out)
 {
 	*out = 0;
+	if (!al->subs.empty()) return map_batch_group(al, bases, offsets, n_reads, out);
 	CK(cudaSetDevice(al->device));
 	for (uint32_t i = 0; i < n_reads; ++i) {
 		uint64_t l = offsets[i + 1] - offsets[i];

@@ -56,7 +56,7 @@ N_STAGES = 12
 
 EXPORTS = ["mmg_host_alloc", "mmg_host_free", "mmg_set_opt", "mmg_mapopt_update", "mmg_index_open", "mmg_index_build", "mmg_index_build_on", "mmg_debug_int32_peak", "mmg_index_dump", "mmg_index_destroy",
            "mmg_index_info", "mmg_index_seq_name", "mmg_index_seq_len", "mmg_index_name2id", "mmg_index_getseq",
-           "mmg_index_entries", "mmg_aligner_create", "mmg_aligner_destroy", "mmg_aligner_set", "mmg_map_batch",
+           "mmg_index_entries", "mmg_aligner_create", "mmg_aligner_create_multi", "mmg_aligner_destroy", "mmg_aligner_set", "mmg_map_batch",
            "mmg_batch_upload", "mmg_batch_run", "mmg_batch_fetch", "mmg_batch_n_reads", "mmg_batch_n_hits",
            "mmg_batch_hit_off", "mmg_batch_hits", "mmg_batch_n_cigar", "mmg_batch_cigar", "mmg_gen_cs",
            "mmg_gen_md", "mmg_gen_tags", "mmg_debug_logf", "mmg_batch_destroy", "mmg_batch_stats", "mmg_stage_times", "mmg_stage_name",
@@ -95,6 +95,7 @@ class Lib:
         L.mmg_index_getseq.argtypes = [c_vp, c_u32, c_u32, c_u32, c_vp]
         L.mmg_index_entries.restype = c_u64; L.mmg_index_entries.argtypes = [c_vp, c_vp, c_vp, c_u64]
         L.mmg_aligner_create.argtypes = [c_vp, P(MapOpt), c_int, P(c_vp)]
+        L.mmg_aligner_create_multi.argtypes = [c_vp, P(MapOpt), c_vp, c_int, P(c_vp)]
         L.mmg_aligner_destroy.argtypes = [c_vp]
         L.mmg_aligner_set.argtypes = [c_vp, c_cp, c_i64]
         L.mmg_map_batch.argtypes = [c_vp, c_vp, c_vp, c_u32, P(c_vp)]
@@ -250,10 +251,19 @@ class Batch:
 
 
 class DeviceAligner:
-    def __init__(self, lib, index, mo, device=0):
+    """One aligner on one GPU (`device`), or - with `devices=[...]` - one aligner that replicates the index on several
+    GPUs of the box, shards every batch by bases over them and gathers the results in read order."""
+
+    def __init__(self, lib, index, mo, device=0, devices=None):
         self.lib, self.index = lib, index
         h = c_vp()
-        lib.check(lib.L.mmg_aligner_create(index.h, ctypes.byref(mo), device, ctypes.byref(h)))
+        if devices is not None and len(devices) > 1:
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            lib.check(lib.L.mmg_aligner_create_multi(index.h, ctypes.byref(mo), dv.ctypes.data, len(dv), ctypes.byref(h)))
+        else:
+            if devices is not None and len(devices) == 1:
+                device = int(devices[0])
+            lib.check(lib.L.mmg_aligner_create(index.h, ctypes.byref(mo), device, ctypes.byref(h)))
         self.h = h
 
     def close(self):

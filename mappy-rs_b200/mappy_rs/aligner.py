@@ -157,7 +157,7 @@ class Aligner:
 
     def __init__(self, fn_idx_in=None, preset=None, k=None, w=None, min_cnt=None, min_chain_score=None, min_dp_score=None,
                  bw=None, best_n=None, n_threads=3, fn_idx_out=None, max_frag_len=None, extra_flags=None, seq=None, scoring=None,
-                 device=0, _lib=None, _tune=None):
+                 device=0, devices=None, _lib=None, _tune=None):
         lib = self._lib = _lib or _mmg.Lib()
         io, mo = _mmg.IdxOpt(), _mmg.MapOpt()
         lib.check(lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mo)))                     # lib.rs:333
@@ -194,7 +194,8 @@ class Aligner:
         self._io, self._mo = io, mo
         self._names = [self._index.seq_name(i) for i in range(self._index.n_seq)]
         self._lens = [self._index.seq_len(i) for i in range(self._index.n_seq)]
-        self._aligner = _mmg.DeviceAligner(lib, self._index, mo, device=device)   # uploads the index once; raises without a GPU
+        # uploads the index once (devices=[...]: replicated over NVLink, batches sharded by bases); raises without a GPU
+        self._aligner = _mmg.DeviceAligner(lib, self._index, mo, device=device, devices=devices)
         for key, val in (_tune or {}).items():   # device arena sizes (not mapping semantics)
             self._aligner.set(key, val)
         self._lock = threading.Lock()

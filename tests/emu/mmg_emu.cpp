@@ -15,7 +15,11 @@ thread_local unsigned char *emu_dyn_smem;
 struct emu_stream_st { int dummy; };
 struct emu_event_st { std::chrono::steady_clock::time_point t; };
 static const char *emu_err = "no error";
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+/* MMG_EMU_DEVICES emulated devices (default 1): they share the host's memory, so multi-device host logic can be tested */
+cudaError_t cudaGetDeviceCount(int *n) { const char *e = getenv("MMG_EMU_DEVICES"); *n = e ? atoi(e) : 1; return cudaSuccess; }
+cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+cudaError_t cudaMemcpyPeer(void *d, int, const void *s, int, size_t n) { memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { memset(p, 0, sizeof(*p)); const char *e = getenv("MMG_EMU_SMS"); p->multiProcessorCount = e ? atoi(e) : 4; p->totalGlobalMem = (size_t)8 << 30; p->sharedMemPerBlockOptin = 227 * 1024; strcpy(p->name, "mmg-emu"); p->major = 10; return cudaSuccess; }

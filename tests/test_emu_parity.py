@@ -444,3 +444,40 @@ def test_cs_and_md_tags_match_oracle(emu_lib, oracle_mod):
         assert parity.compare_tags(c, buf, offs, dev, 1) == []
     finally:
         c.close()
+
+
+def test_multi_device_aligner_equals_single_device(emu_lib, oracle_mod):
+    """mmg_aligner_create_multi: the index replicated on three (emulated) devices, a batch sharded by bases over them on
+    three host threads and gathered in read order must give the bytes of the one-device result (and of the oracle),
+    CIGAR offsets rebased, in both modes; empty and tiny batches included."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, ctypes
+import numpy as np
+sys.path[:0] = [os.path.join(%(root)r, "oracle"), os.path.join(%(root)r, "tests"), os.path.join(%(root)r, "mappy-rs_b200")]
+import data_gen, parity
+from mappy_rs import _mmg
+lib = _mmg.Lib(%(emu)r)
+ref, coff, names, seqs = parity.random_reference(11, [150000, 60000])
+buf, offs, _ = data_gen.make_reads(12, ref, coff, 61, 300, 5000)
+for cigar in (False, True):
+    c = parity.Case(lib, names, seqs, cigar=cigar)
+    one = c.aligner.map_batch(buf, offs)
+    multi = _mmg.DeviceAligner(lib, c.index, c.mopt, devices=[0, 1, 2])
+    for n in (61, 2, 1, 0):
+        sub_b, sub_o = buf[:int(offs[n])], offs[:n + 1]
+        want = c.aligner.map_batch(sub_b, sub_o) if n != 61 else one
+        got = multi.map_batch(sub_b, sub_o)
+        assert parity.compare_hits(got, want) == [], (cigar, n)
+        assert np.array_equal(got.hit_off, want.hit_off) and got.stats["n_bases"] == want.stats["n_bases"]
+    ora = c.oracle.map_batch(buf, offs, 4)
+    assert parity.compare_hits(multi.map_batch(buf, offs), ora) == []
+    multi.close()
+    c.close()
+print("multi-device ok")
+'''
+    from conftest import ROOT, EMU_LIB
+    env = dict(os.environ, MMG_EMU_DEVICES="3")
+    r = subprocess.run([sys.executable, "-c", code % {"root": ROOT, "emu": EMU_LIB}], env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "multi-device ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
