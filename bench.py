@@ -287,6 +287,65 @@ def measure_mode(args, lib, idx, mopt_base, cigar, views, n_reads, n_bases, loca
     return out, res0, lat
 
 
+def run_group(args, lib, io, mopt, idx, ref, coff, names, preset, hbuf, offs, rank, local_rank, world, barrier, host_pg):
+    """N > 1 only, after the per-rank (weak-scaling) legs: ONE process - rank 0 - drives all N GPUs through the
+    product's multi-device aligner (mmg_aligner_create_multi): the index is built once and replicated over NVLink with
+    peer copies, one common batch of N x reads_per_gpu reads (the shards the ranks mapped, concatenated) is sharded by
+    bases inside mmg_map_batch and the results are gathered on the host in read order.  The other ranks release their
+    GPUs and wait.  This is the reference's own shape (one aligner, N workers on a shared index, lib.rs:545-553)."""
+    import torch
+    import torch.distributed as dist
+    from mappy_rs import _mmg
+    import data_gen
+    idx.close()
+    torch.cuda.empty_cache()
+    barrier()
+    out = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        gidx = _mmg.Index.build(lib, io, names, contig_seqs(ref, coff, names), device=0)
+        m2 = _mmg.MapOpt.from_buffer_copy(mopt)
+        m2.flag = 0 if args.mapping_only else 4
+        lib.check(lib.L.mmg_mapopt_update(ctypes.byref(m2), gidx.h))
+        al = _mmg.DeviceAligner(lib, gidx, m2, devices=list(range(world)))
+        setup_s = time.perf_counter() - t0
+        bufs, lens = [hbuf.numpy()], [np.diff(offs.astype(np.int64))]
+        big = args.workload == "human" or args.ref == "human"
+        for r in range(1, world):   # the reads the other ranks mapped (same seeds)
+            if args.workload == "hifi":
+                b, o, _ = data_gen.make_reads(5 + 1000 * r, ref, coff, args.reads, 10000, 25000, len_mean=15000.0, len_sd=2000.0, p_sub=0.002, p_ins=0.0015, p_del=0.0015)
+            else:
+                b, o, _ = data_gen.make_reads((4 if big else 2) + 1000 * r, ref, coff, args.reads, 1000, 10000, p_sub=0.03, p_ins=0.02, p_del=0.03)
+                if args.workload == "prefix":
+                    b, o = data_gen.prefixes(b, o, 400)
+            bufs.append(b), lens.append(np.diff(o.astype(np.int64)))
+        n_all = int(sum(len(x) for x in lens))
+        goffs = np.zeros(n_all + 1, dtype=np.uint64)
+        goffs[1:] = np.cumsum(np.concatenate(lens))
+        gbuf = torch.empty(int(goffs[-1]), dtype=torch.uint8, pin_memory=True)
+        pos = 0
+        for b in bufs:
+            gbuf.numpy()[pos:pos + len(b)] = b
+            pos += len(b)
+        gh = gbuf.numpy()
+        steps = max(2, min(args.steps, 3))
+        al.map_batch(gh, goffs, zero_copy=True).close()
+        t0 = time.perf_counter()
+        nh = 0
+        for _ in range(steps):
+            r = al.map_batch(gh, goffs, zero_copy=True)
+            nh = len(r.hits)
+            r.close()
+        dt = (time.perf_counter() - t0) / steps
+        out = {"value": n_all / dt, "unit": "reads/s", "ms_per_step": dt * 1e3, "n_gpus": world, "reads_per_step": n_all, "bases_per_step": int(goffs[-1]), "hits": nh, "steps": steps,
+               "mbases_per_s": int(goffs[-1]) / dt / 1e6, "setup_s": setup_s,
+               "what": "one process, one multi-device aligner (mmg_aligner_create_multi): index built once on GPU 0 and peer-copied to the others, ONE batch of all ranks' reads sharded by bases, results gathered on the host in read order; host buffers in, host results out (end to end)"}
+        al.close()
+        gidx.close()
+    dist.barrier(group=host_pg)   # the waiting ranks block on the host (gloo): no NCCL kernel spins on the GPUs rank 0 is timing
+    return out
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -294,8 +353,10 @@ def run_ours(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the mapping path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    host_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_pg = dist.new_group(backend="gloo")   # host-side barrier for the one-process multi-device leg
     lib = _mmg.Lib()
     cfg = config_of(args)
     ref, coff, names, buf, offs, preset = workload(args, rank)
@@ -350,6 +411,9 @@ def run_ours(args, rank, local_rank, world):
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
+    group = None
+    if world > 1 and not args.no_group:
+        group = run_group(args, lib, io, mopt, idx, ref, coff, names, preset, hbuf, offs, rank, local_rank, world, barrier, host_pg)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -366,6 +430,8 @@ def run_ours(args, rank, local_rank, world):
         "host_gap_ms_per_step": prim["host_gap_ms_per_step"], "host_gap_note": prim["host_gap_note"],
         "clocks": sampler.summary(),
     }
+    if group is not None:
+        out["group"] = group
     if second is not None:
         out["mapping_only"] = {k: second[k] for k in ("value", "ms_per_step", "mbases_per_s", "e2e", "gpu_launches", "roofline", "int32_roofline", "stage_ms_per_step",
                                                       "counters", "per_rank_ms_per_step", "host_gap_ms_per_step")}
@@ -424,6 +490,7 @@ def main():
     ap.add_argument("--cigar", action="store_true", help="(default) MM_F_CIGAR on: what mappy-rs itself always runs")
     ap.add_argument("--mapping-only", action="store_true", help="primary mode = chain-level mapping without base alignment (configs[1]'s mode)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the mapping_only leg of the default line")
+    ap.add_argument("--no-group", action="store_true", help="N > 1: skip the one-process multi-device leg (one common batch sharded over all GPUs, gathered on rank 0)")
     args = ap.parse_args()
     if args.reads <= 0:
         args.reads = {"config1": 200000, "human": 250000, "prefix": 400000, "hifi": 40000}[args.workload]

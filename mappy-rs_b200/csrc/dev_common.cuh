@@ -7,7 +7,7 @@
 #ifdef MMG_EMU
 #include "mmg_emu.h"
 #define MMG_LAUNCH(kernel, grid, block, smem, stream, ...) \
-	emu_launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
+	(emu_kernel_name = #kernel, emu_launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); }))
 #define MMG_DYN_SMEM(name) unsigned char *name = emu_dyn_smem
 #else
 #include <cuda_runtime.h>

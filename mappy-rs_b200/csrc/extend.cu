@@ -403,6 +403,7 @@ ext_prep_kernel(ChunkDev c, DevIndex di, DevOpt o, ExtBufs xb, uint32_t r0, uint
 					o, scr, &qe, &te);
 				if (score < o.min_dp_max) ok = false;
 			}
+			__syncwarp();   /* every lane has read xr[i].state before lane 0 changes it */
 			if (lane == 0) {
 				ExtReg *x = &xr[i];
 				x->n_jobs = 0;

@@ -400,6 +400,7 @@ int mmg_index_build_device(int w, int k, int b, int flag, int n_seq, const char 
 		uint32_t hb = 4;
 		const uint64_t inv_load = getenv("MMG_TABLE_INV_LOAD") ? (uint64_t)atoi(getenv("MMG_TABLE_INV_LOAD")) : 4; /* slots per key (tuning experiment hook) */
 		while (((uint64_t)1 << hb) < n_keys * (inv_load < 2 ? 2 : inv_load)) ++hb;
+		if (n_multi >> 32) { mmg_set_error("index has %llu multi-occurrence positions: more than 2^32 are not supported", (unsigned long long)n_multi); rc = MMG_ECUDA; goto fail; }
 		idx->hbits = hb, idx->n_keys = n_keys, idx->n_pos = n_multi;
 		const uint64_t nslots = (uint64_t)1 << hb;
 		const uint32_t big_cap = 1u << 16;

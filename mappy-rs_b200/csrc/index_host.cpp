@@ -238,6 +238,11 @@ static mmg_index *build_from_seqs(int w, int k, int b, int flag, int n_seq, cons
 		if (j - i > 1) n_pos += j - i;
 		i = j;
 	}
+	if (n_pos >> 32) { /* the flat table stores pos[] offsets in 32 bits (upstream's are per bucket) */
+		mmg_set_error("index has %llu multi-occurrence positions: more than 2^32 are not supported", (unsigned long long)n_pos);
+		delete idx;
+		return 0;
+	}
 	table_alloc(idx, n_keys);
 	idx->pos.reserve(n_pos);
 	for (size_t i = 0; i < all.size();) {
@@ -281,6 +286,11 @@ static mmg_index *load_mmi(FILE *fp)
 		ok = fread(&n, 4, 1, fp) == 1;
 		if (!ok) break;
 		uint64_t base = idx->pos.size();
+		if ((base + (n > 0 ? (uint64_t)n : 0)) >> 32) { /* the flat table stores global pos[] offsets in 32 bits */
+			mmg_set_error("index has more than 2^32 multi-occurrence positions: not supported");
+			ok = false;
+			break;
+		}
 		if (n > 0) {
 			idx->pos.resize(base + n);
 			ok = fread(&idx->pos[base], 8, n, fp) == (size_t)n;

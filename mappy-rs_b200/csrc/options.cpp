@@ -58,7 +58,31 @@ extern "C" int mmg_set_opt(const char *preset, mmg_idxopt_t *io, mmg_mapopt_t *m
 		mo->min_dp_max = 200;
 		return MMG_OK;
 	}
-	mmg_set_error("preset '%s' is outside the supported path (map-ont, map-hifi)", preset);
+	if (!strcmp(preset, "ava-ont")) { /* options.c; NO_DIAG | NO_DUAL need a query name, which this path never has */
+		io->flag = 0, io->k = 15, io->w = 5;
+		mo->flag |= 0x001 | 0x002 | MMG_F_ALL_CHAINS | MMG_F_NO_LJOIN;
+		mo->min_chain_score = 100, mo->pri_ratio = 0.0f, mo->max_chain_skip = 25;
+		mo->bw = mo->bw_long = 2000;
+		mo->occ_dist = 0;
+		return MMG_OK;
+	}
+	if (!strncmp(preset, "asm", 3)) { /* assembly-to-reference: chaining by range-minimum query (MM_F_RMQ) */
+		int a, b, q, q2, e, w = 19;
+		if (!strcmp(preset, "asm5")) a = 1, b = 19, q = 39, q2 = 81, e = 3;
+		else if (!strcmp(preset, "asm10")) a = 1, b = 9, q = 16, q2 = 41, e = 2;
+		else if (!strcmp(preset, "asm20")) a = 1, b = 4, q = 6, q2 = 26, e = 2, w = 10;
+		else { mmg_set_error("unknown preset '%s'", preset); return MMG_EINVAL; }
+		io->flag = 0, io->k = 19, io->w = (short)w;
+		mo->bw = 1000, mo->bw_long = 100000;
+		mo->max_gap = 10000;
+		mo->flag |= MMG_F_RMQ;
+		mo->min_mid_occ = 50, mo->max_mid_occ = 500;
+		mo->min_dp_max = 200;
+		mo->best_n = 50;
+		mo->a = a, mo->b = b, mo->q = q, mo->q2 = q2, mo->e = e, mo->e2 = 1, mo->zdrop = mo->zdrop_inv = 200;
+		return MMG_OK;
+	}
+	mmg_set_error("preset '%s' is outside the supported path (map-ont / lr, map-hifi / map-ccs, ava-ont, asm5 / asm10 / asm20)", preset);
 	return MMG_EINVAL;
 }
 

@@ -315,7 +315,9 @@ static int aligner_create_on(const mmg_index *idx, const mmg_mapopt_t *mo, int d
 	}
 	if (device < 0 || device >= n_dev) { mmg_set_error("device %d out of range (%d devices)", device, n_dev); return MMG_EINVAL; }
 	if ((mo->flag & MMG_F_CIGAR) && (idx->flag & MMG_I_NO_SEQ)) { mmg_set_error("index has no sequence but CIGAR was requested"); return MMG_ENOSEQ; }
-	const int64_t unsup = 0x80LL | 0x100LL | 0x200LL | 0x1000LL | 0x2000LL | MMG_F_FOR_ONLY | MMG_F_REV_ONLY | 0x400000LL | 0x20000000LL | MMG_F_RMQ | 0x100000000LL | 0x1LL | 0x2LL;
+	/* MM_F_NO_DIAG (0x1) and MM_F_NO_DUAL (0x2) compare the query NAME with the target names; mappy-rs passes qname = NULL
+	 * (crate minimap2 Aligner::map), so they have no effect on this path and are accepted (preset ava-ont sets them) */
+	const int64_t unsup = 0x80LL | 0x100LL | 0x200LL | 0x1000LL | 0x2000LL | MMG_F_FOR_ONLY | MMG_F_REV_ONLY | 0x400000LL | 0x20000000LL | 0x100000000LL;
 	if (mo->flag & unsup) { mmg_set_error("mapping flag 0x%llx selects a code path outside the supported long-read path", (unsigned long long)(mo->flag & unsup)); return MMG_EUNSUP; }
 	if (idx->flag & MMG_I_HPC) { mmg_set_error("homopolymer-compressed indexes are not supported"); return MMG_EUNSUP; }
 	if (idx->offs.back() >= ((uint64_t)1 << 35)) { mmg_set_error("references of 2^35 bases or more are not supported"); return MMG_EUNSUP; }
@@ -505,7 +507,7 @@ int mmg_batch_upload(mmg_aligner *al, const char *bases, const uint64_t *offsets
 		mmg_batch_destroy(b);
 		return MMG_ENOMEM;
 	}
-	b->hits_cap = (uint64_t)n_reads * 6 + 1024;
+	b->hits_cap = (uint64_t)n_reads * (uint64_t)(al->mo.best_n + 4 > 6 ? al->mo.best_n + 4 : 6) + 1024;   /* primaries + best_n secondaries; the streamed path grows on demand */
 	if (cudaMalloc((void**)&b->d_hits, b->hits_cap * sizeof(mmg_hit_t)) != cudaSuccess) { mmg_set_error("cudaMalloc failed for the result pool"); mmg_batch_destroy(b); return MMG_ENOMEM; }
 	if (al->mo.flag & MMG_F_CIGAR) {
 		b->cigar_cap = b->n_bases / 2 + ((uint64_t)1 << 16) + (uint64_t)n_reads * 8;
@@ -679,7 +681,7 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 	CK(cudaStreamSynchronize(st));
 	/* isolated-anchor filter (exact under these conditions, see seed.cu): worth its two passes over the hits only
 	 * when reads carry many anchors, i.e. on large references */
-	if (al->anchor_filter && al->mo.min_cnt >= 2 && al->mo.min_chain_score > al->idx->k && c.n_reads > 0 &&
+	if (al->anchor_filter && !(al->mo.flag & MMG_F_RMQ) && al->mo.min_cnt >= 2 && al->mo.min_chain_score > al->idx->k && c.n_reads > 0 &&
 	    a_total > (uint64_t)c.n_reads * 64 && (a_total >> 5) + c.n_reads + 1 <= al->cap_keep_words) {
 		STAGE_BEGIN();
 		CK(cudaMemcpyAsync(c.af_off, c.a_off, (size_t)(c.n_reads + 1) * 8, cudaMemcpyDeviceToDevice, st));
@@ -724,7 +726,8 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 				const uint32_t a = h ? mid : s0, bnd = h ? s1 : mid;
 				launch_expand(ch, al->di, al->dopt, a, bnd, al->n_sms, sh, work + wi++);
 				launch_sort(ch, al->di, a, bnd, al->n_sms, sh, work + wi); wi += 5;
-				launch_chain(ch, al->dopt, a, bnd, al->n_sms, sh, work + wi++);
+				if (al->mo.flag & MMG_F_RMQ) launch_chain_rmq(ch, al->dopt, a, bnd, al->rmq_nodes, al->n_sms, sh, work + wi++);
+				else launch_chain(ch, al->dopt, a, bnd, al->n_sms, sh, work + wi++);
 				launch_backtrack(ch, al->dopt, a, bnd, al->n_sms, sh, work + wi++);
 				launch_rechain(ch, al->dopt, a, bnd, al->rmq_nodes, al->n_sms, sh, work + wi++);
 			}
@@ -734,7 +737,10 @@ static int run_chunk(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t r0, st
 		} else {
 		STAGE_BEGIN(); launch_expand(c, al->di, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_EXPAND);
 		STAGE_BEGIN(); launch_sort(c, al->di, s0, s1, al->n_sms, st, work + wi); wi += 5; STAGE_END(ST_SORT);
-		STAGE_BEGIN(); launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_CHAIN);
+		STAGE_BEGIN();
+		if (al->mo.flag & MMG_F_RMQ) launch_chain_rmq(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++);   /* asm presets: mm_lchain_rmq */
+		else launch_chain(c, al->dopt, s0, s1, al->n_sms, st, work + wi++);
+		STAGE_END(ST_CHAIN);
 		STAGE_BEGIN(); launch_backtrack(c, al->dopt, s0, s1, al->n_sms, st, work + wi++); STAGE_END(ST_BACKTRACK);
 		STAGE_BEGIN(); launch_rechain(c, al->dopt, s0, s1, al->rmq_nodes, al->n_sms, st, work + wi++); STAGE_END(ST_RECHAIN);
 		}

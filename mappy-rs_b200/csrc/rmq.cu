@@ -425,6 +425,34 @@ rechain_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, uin
 	if (lane == 0 && tot_rechain) atomicAdd(&c.stats[9], tot_rechain);
 }
 
+/* MM_F_RMQ (the asm5 / asm10 / asm20 presets): map.c mm_map_frag chains with mm_lchain_rmq instead of mm_lchain_dp.
+ * Same routine as the re-chain step, on the sorted anchors of the read, band bw; backtrack_kernel follows as usual. */
+__global__ void __launch_bounds__(CHAIN_WARPS * 32)
+chain_rmq_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, uint32_t *work)
+{
+	const int lane = mmg_lane();
+	for (;;) {
+		uint32_t r = r0 + mmg_next_item(work);
+		if (r >= r1) break;
+		r = mmg_read_of(c, r);
+		const int n = (int)c.n_a[r];
+		const uint64_t ab = c.a_off[r] - c.a_off0;
+		if (lane == 0 && n > 0)
+			dev_lchain_rmq(o.max_gap, o.rmq_inner_dist, o.bw, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
+			               n, c.bx + ab, c.by + ab, c.f + ab, c.p + ab, c.t + ab, nodes + 2 * ab + 2 * (uint64_t)r);
+		__syncwarp();
+	}
+}
+
+int launch_chain_rmq(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, void *nodes, int n_sms, cudaStream_t st, uint32_t *work)
+{
+	int grid = n_sms * 8, need = ((int)(r1 - r0) + CHAIN_WARPS - 1) / CHAIN_WARPS;
+	if (grid > need) grid = need;
+	if (grid < 1) grid = 1;
+	MMG_LAUNCH(chain_rmq_kernel, grid, CHAIN_WARPS * 32, 0, st, c, o, r0, r1, (RNode*)nodes, work);
+	return 0;
+}
+
 int launch_rechain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, void *nodes, int n_sms, cudaStream_t st, uint32_t *work)
 {
 	int grid = n_sms * 8, need = ((int)(r1 - r0) + CHAIN_WARPS - 1) / CHAIN_WARPS;

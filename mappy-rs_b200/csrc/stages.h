@@ -20,6 +20,7 @@ int launch_expand(const ChunkDev &c, const DevIndex &di, const DevOpt &o, uint32
 int launch_sort(const ChunkDev &c, const DevIndex &di, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
 void mmg_sort_set_small_max(int v); /* reads with more anchors take the radix pass (tuning knob "sort_small_max") */
 int launch_chain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
+int launch_chain_rmq(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, void *nodes, int n_sms, cudaStream_t st, uint32_t *work);
 int launch_backtrack(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, int n_sms, cudaStream_t st, uint32_t *work);
 #define RMQ_NODE_BYTES 40 /* sizeof(RNode) in rmq.cu; the arena holds 2 * (anchors + reads) nodes */
 int launch_rechain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, void *nodes, int n_sms, cudaStream_t st, uint32_t *work);

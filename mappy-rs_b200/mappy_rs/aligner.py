@@ -23,6 +23,8 @@ import numpy as np
 from . import _mmg
 
 _WORK_QUEUE_CAP = 50000   # lib.rs:429-430
+_DRAIN_BASES = 32 << 20   # the worker starts a device batch as soon as this many bases are queued ...
+_IDLE_S = 0.02            # ... or the producer has pushed nothing for this long (a slow generator still streams)
 _CIGAR_OPS = "MIDNSHP=X"
 
 
@@ -279,24 +281,31 @@ class Aligner:
                                                             (hasattr(seqs, "__getitem__") and hasattr(seqs, "__len__"))):
             raise TypeError("Unsupported batch type, pass a list, iter, generator or tuple")
         res_iter = AlignmentBatchResultIter()
+        self._streamed_probe = lambda: len(res_iter._q)   # results already waiting for the consumer (tests)
         work = collections.deque()          # the bounded work queue of lib.rs:301,429
         cv = threading.Condition()
-        state = {"done": False, "abort": False}
+        state = {"done": False, "abort": False, "bases": 0, "last_push": time.monotonic()}
 
         def worker():
+            """The reference's N workers pop reads while the producer is still pushing (lib.rs:559-633).  Here one
+            worker hands device-sized batches to the GPU as soon as enough bases are queued, the queue is full, the
+            producer pauses, or the input ends - results reach the consumer while the input is still being produced."""
             try:
                 while True:
                     with cv:
-                        # drain when the producer is done or the queue is full (large device batches; and the
-                        # documented 50000-entry limit of the work queue stays observable)
-                        while not state["done"] and len(work) < _WORK_QUEUE_CAP:
-                            cv.wait(0.01)
-                        items = list(work)
-                        work.clear()
-                        done = state["done"]
-                        cv.notify_all()
+                        while not state["abort"]:
+                            n = len(work)
+                            if state["done"] or n >= _WORK_QUEUE_CAP or state["bases"] >= _DRAIN_BASES or \
+                               (n and time.monotonic() - state["last_push"] >= _IDLE_S):
+                                break
+                            cv.wait(_IDLE_S / 2 if n else 0.05)
                         if state["abort"]:   # the producer raised: nothing is returned to the caller (lib.rs:847-866 return early)
                             break
+                        items = list(work)
+                        work.clear()
+                        state["bases"] = 0
+                        done = state["done"]
+                        cv.notify_all()
                     if items:
                         per_read = self._map_reads([s for _, s in items], True, False)   # cs=true, md=false: lib.rs:587-593
                         res_iter._put([(m, d) for m, (d, _) in zip(per_read, items)])
@@ -326,11 +335,17 @@ class Aligner:
                             raise RuntimeError(
                                 "Internal error adding data to work queue, without backoff. Work(({id_num}, ..)) {id_num}. "
                                 "Is your fastq batch larger than 50000? Perhaps try `map_batch` with back_off=True?".format(id_num=id_num))
+                        # lib.rs:871-885 sleeps 50 ms doubling, six times, and then DROPS the read with a message on
+                        # stderr; here the producer waits until the worker has taken the queue: the 50000-entry limit
+                        # is honoured and no read is lost
                         cv.notify_all()
-                        deadline = time.time() + 3.15   # 50 ms doubling, 6 attempts (lib.rs:871-885)
-                        while len(work) >= _WORK_QUEUE_CAP and time.time() < deadline:
+                        while len(work) >= _WORK_QUEUE_CAP and not res_iter._finished:
                             cv.wait(0.05)
                     work.append((data, seq))
+                    state["bases"] += len(seq)
+                    state["last_push"] = time.monotonic()
+                    if state["bases"] >= _DRAIN_BASES or len(work) >= _WORK_QUEUE_CAP:
+                        cv.notify_all()
             ok = True
         finally:
             with cv:

@@ -10,6 +10,7 @@
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
 thread_local unsigned char *emu_dyn_smem;
+thread_local const char *emu_kernel_name = "?";
 
 /* ---------------- host runtime shim ---------------- */
 struct emu_stream_st { int dummy; };
@@ -174,7 +175,7 @@ uint64_t emu_collective(int op, unsigned mask, uint64_t v, int arg, int width)
 	int w = f->tid >> 5, l = f->tid & 31;
 	WarpState *ws = &b->warps[w];
 	if (ws->arrived == 0) ws->op = op, ws->width = width, ws->mask = mask;
-	else if (ws->op != op) { fprintf(stderr, "[emu] divergent collective in block %u warp %d: op %d vs %d\n", blockIdx.x, w, ws->op, op); abort(); }
+	else if (ws->op != op) { fprintf(stderr, "[emu] divergent collective in %s, block %u warp %d: op %d vs %d\n", emu_kernel_name, blockIdx.x, w, ws->op, op); abort(); }
 	ws->vals[l] = v;
 	ws->args[l] = arg;
 	ws->arrived |= 1u << l;

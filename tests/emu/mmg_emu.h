@@ -80,6 +80,7 @@ template<typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncA
 
 /* ---- launch ---- */
 void emu_launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()> &body);
+extern thread_local const char *emu_kernel_name;   /* name of the kernel being emulated (diagnostics) */
 extern thread_local unsigned char *emu_dyn_smem;
 
 /* ---- rendezvous primitives ---- */

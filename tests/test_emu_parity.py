@@ -481,3 +481,33 @@ print("multi-device ok")
     env = dict(os.environ, MMG_EMU_DEVICES="3")
     r = subprocess.run([sys.executable, "-c", code % {"root": ROOT, "emu": EMU_LIB}], env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "multi-device ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+@pytest.mark.parametrize("preset,cigar", [("ava-ont", False), ("ava-ont", True), ("asm20", True), ("asm5", True)])
+def test_other_presets_reachable_by_string(emu_lib, oracle_mod, preset, cigar):
+    """Presets a caller can name through `Aligner(preset=...)` (/root/reference/src/lib.rs:334-337): ava-ont (all
+    chains, no long join, w = 5; its NO_DIAG / NO_DUAL flags need a query name and are inert here) and asm5/10/20
+    (MM_F_RMQ: chaining by range-minimum query instead of mm_lchain_dp, best_n = 50, wide bands)."""
+    ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
+    c = parity.Case(emu_lib, names, seqs, cigar=cigar, preset=preset)
+    try:
+        if preset.startswith("asm"):
+            buf, offs, _ = data_gen.make_reads(58, ref, coff, 16, 3000, 20000, p_sub=0.01, p_ins=0.003, p_del=0.003)
+        else:
+            buf, offs = data_gen.make_sv_reads(57, ref, coff, 30)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_stats(dev, ora) == []
+        assert parity.compare_hits(dev, ora) == []
+        assert len(ora.hits) >= len(offs) - 1
+    finally:
+        c.close()
+
+
+def test_unsupported_presets_are_rejected_not_approximated(emu_lib):
+    import ctypes
+    from mappy_rs import _mmg
+    io, mo = _mmg.IdxOpt(), _mmg.MapOpt()
+    emu_lib.check(emu_lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mo)))
+    for preset in (b"sr", b"splice", b"map-pb", b"nonsense"):
+        assert emu_lib.L.mmg_set_opt(preset, ctypes.byref(io), ctypes.byref(mo)) < 0

@@ -190,3 +190,21 @@ def test_four_tuple_scoring_equals_ksw_extz2(gpu_lib, oracle_mod, scoring):
         assert parity.compare_hits(dev2, ora2) == []
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("preset", ["ava-ont", "asm20", "asm10", "asm5"])
+def test_other_presets_reachable_by_string(gpu_lib, oracle_mod, preset):
+    """ava-ont and the asm presets (MM_F_RMQ chaining) with CIGAR, against the oracle."""
+    ref, coff, names, seqs = parity.random_reference(41, [3000000, 1500000], n_repeats=600, rep_min=300, rep_max=6000, rep_div=0.03)
+    c = parity.Case(gpu_lib, names, seqs, cigar=True, preset=preset)
+    try:
+        if preset.startswith("asm"):
+            buf, offs, _ = data_gen.make_reads(58, ref, coff, 300, 5000, 60000, p_sub=0.01, p_ins=0.003, p_del=0.003)
+        else:
+            buf, offs = data_gen.make_sv_reads(51, ref, coff, 1500, 400, 6000)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, NT)
+        assert parity.compare_stats(dev, ora) == []
+        assert parity.compare_hits(dev, ora) == []
+    finally:
+        c.close()

@@ -168,3 +168,47 @@ def test_constructor_and_unimplemented_corners(emu_lib):
         assert a.map_no_op("ACGT")[0].ctg == "Hello"
     finally:
         a.close()
+
+
+def test_results_stream_while_the_producer_is_still_feeding(aligner):
+    """/root/reference/src/lib.rs:559-633, 972-991: workers map while the producer is still pushing, so a consumer can
+    read results before a slow generator is exhausted.  The device worker starts a batch when the producer pauses."""
+    import threading
+    import time
+    a, _ = aligner
+    a.enable_threading(2)
+    recs = contig_records(2)
+    gate = threading.Event()
+    produced = []
+
+    def slow():
+        for i, r in enumerate(recs):
+            if i == 4:
+                gate.wait(60)          # the producer stalls until the consumer has seen the first results
+            produced.append(i)
+            yield r
+
+    out = []
+    box = {}
+
+    def feed():
+        box["it"] = a.map_batch(slow())
+
+    th = threading.Thread(target=feed)
+    th.start()
+    deadline = time.time() + 60
+    while "it" not in box and len(produced) < 4 and time.time() < deadline:
+        time.sleep(0.01)
+    # map_batch returns only when the producer is done (lib.rs:771-906 runs it on the caller's thread); the iterator it
+    # will return is fed by the worker meanwhile: wait until the first four reads have been mapped, then open the gate
+    while time.time() < deadline:
+        w = [t for t in getattr(a, "_workers", []) if t.is_alive()]
+        if len(produced) >= 4 and getattr(a, "_streamed_probe", lambda: 0)() >= 4:
+            break
+        time.sleep(0.02)
+    early = getattr(a, "_streamed_probe", lambda: 0)()
+    gate.set()
+    th.join(120)
+    out = list(box["it"])
+    assert len(out) == len(recs) and early >= 4, (len(out), early)
+    assert sorted(d["id"] for _, d in out) == list(range(len(recs)))
