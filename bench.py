@@ -413,7 +413,14 @@ def run_ours(args, rank, local_rank, world):
         sampler.join(timeout=2)
     group = None
     if world > 1 and not args.no_group:
-        group = run_group(args, lib, io, mopt, idx, ref, coff, names, preset, hbuf, offs, rank, local_rank, world, barrier, host_pg)
+        try:
+            group = run_group(args, lib, io, mopt, idx, ref, coff, names, preset, hbuf, offs, rank, local_rank, world, barrier, host_pg)
+        except Exception as e:   # the per-rank lines above stay valid; the failure is reported, not hidden
+            group = {"error": str(e)[:300]}
+            try:
+                dist.barrier(group=host_pg)
+            except Exception:
+                pass
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

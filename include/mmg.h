@@ -174,6 +174,26 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t value);
  * copy of the results happen inside this call. */
 int mmg_map_batch(mmg_aligner *al, const char *bases, const uint64_t *offsets, uint32_t n_reads, mmg_batch **out);
 
+/* ---- streaming -------------------------------------------------------------
+ * replaces the work queue, the worker threads and the result queue behind `enable_threading` / `map_batch` / the
+ * result iterator (src/lib.rs:297-309, 541-636, 771-906, 972-991).  mmg_submit copies the reads into page-locked
+ * staging owned by the library and returns at once (the host may drop its strings, as src/lib.rs:856-866 does after
+ * the push); one worker thread of the aligner maps device-sized batches as soon as enough bases are queued, the
+ * producer pauses (20 ms) or calls mmg_flush; mmg_next hands back one read's hits at a time (1 = a result, 0 = none
+ * within timeout_ms / nothing outstanding, < 0 = error; timeout_ms < 0 waits).  A result stays valid until
+ * mmg_result_release.  submit / flush and next / release may be called from different threads. */
+typedef struct {
+	uint64_t read_id;          /* first_id + position of the read in its mmg_submit call */
+	uint32_t n_hits;
+	const mmg_hit_t *hits;     /* n_hits records in the order mm_map returns them */
+	const uint32_t *cigar;     /* hits[i].cigar_off indexes this pool */
+	void *owner;               /* internal */
+} mmg_result_t;
+int mmg_submit(mmg_aligner *al, const char *bases, const uint64_t *offsets, uint32_t n_reads, uint64_t first_id);
+int mmg_flush(mmg_aligner *al);
+int mmg_next(mmg_aligner *al, mmg_result_t *out, int timeout_ms);
+void mmg_result_release(mmg_aligner *al, mmg_result_t *r);
+
 /* Page-locked host memory for the `bases` buffer of mmg_map_batch: with it the per-chunk host->device copies are
  * asynchronous and overlap the kernels (a pageable buffer is staged by the driver and blocks the submitting thread).
  * Replaces nothing in the reference (its FFI passes one `*const c_char` per read, src/lib.rs:482-488); it is what the

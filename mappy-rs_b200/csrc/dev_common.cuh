@@ -19,6 +19,17 @@
 #include <stdint.h>
 #include "../../include/mmg.h"
 
+/* true the first time it is called on the current device for this flag array: kernel attributes
+ * (cudaFuncSetAttribute) are per device, and a multi-device aligner launches every kernel on several */
+static inline bool mmg_once_per_device(unsigned char *done /* [64] */)
+{
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64 || done[dev]) return false;
+	done[dev] = 1;
+	return true;
+}
+
 #define MMG_FULL 0xffffffffu
 #define MMG_INF64 0xffffffffffffffffULL
 

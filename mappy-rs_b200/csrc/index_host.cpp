@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <zlib.h>
 #include <stdarg.h>
 #include <algorithm>
 #include <thread>
@@ -314,26 +315,39 @@ static mmg_index *load_mmi(FILE *fp)
 	return idx;
 }
 
+/* FASTA / FASTQ, plain or gzip-compressed, as mm_idx_reader_open reads it through kseq + zlib
+ * (/root/reference/src/lib.rs:398; gzread passes uncompressed files through).  The whole file is one index part:
+ * mappy-rs sets batch_size to 2^63 - 1 (src/lib.rs:340). */
 static mmg_index *load_fasta(const char *path, const mmg_idxopt_t *io, int n_threads)
 {
-	FILE *fp = fopen(path, "rb");
+	gzFile fp = gzopen(path, "rb");
 	if (!fp) return 0;
+	gzbuffer(fp, 1 << 20);
 	std::string buf;
-	char tmp[1 << 16];
-	size_t nr;
-	while ((nr = fread(tmp, 1, sizeof(tmp), fp)) > 0) buf.append(tmp, nr);
-	fclose(fp);
+	std::vector<char> tmp(1 << 20);
+	int nr;
+	while ((nr = gzread(fp, tmp.data(), (unsigned)tmp.size())) > 0) buf.append(tmp.data(), (size_t)nr);
+	const bool bad = nr < 0;
+	gzclose(fp);
+	if (bad) { mmg_set_error("error while reading (decompressing) '%s'", path); return 0; }
 	std::vector<std::string> names, seqs;
+	size_t qual_left = 0;       /* FASTQ: quality characters still to skip */
+	bool in_qual = false;
 	for (size_t i = 0; i < buf.size();) {
 		size_t e = buf.find('\n', i);
 		if (e == std::string::npos) e = buf.size();
 		size_t l = e;
 		while (l > i && (buf[l - 1] == '\r' || buf[l - 1] == ' ')) --l;
-		if (l > i && buf[i] == '>') {
+		if (in_qual) { /* kseq: the quality string is as long as the sequence, whatever it contains */
+			qual_left = l - i >= qual_left ? 0 : qual_left - (l - i);
+			if (qual_left == 0) in_qual = false;
+		} else if (l > i && (buf[i] == '>' || buf[i] == '@')) {
 			size_t p = i + 1;
 			while (p < l && buf[p] != ' ' && buf[p] != '\t') ++p;
 			names.push_back(buf.substr(i + 1, p - i - 1));
 			seqs.push_back(std::string());
+		} else if (l > i && buf[i] == '+' && !seqs.empty()) {
+			qual_left = seqs.back().size(), in_qual = qual_left > 0;
 		} else if (l > i && !seqs.empty()) seqs.back().append(buf, i, l - i);
 		i = e + 1;
 	}

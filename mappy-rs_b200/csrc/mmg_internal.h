@@ -61,5 +61,7 @@ int mmg_index_build_device(int w, int k, int b, int flag, int n_seq, const char 
                            int device, mmg_index **out);
 int mmg_index_ensure_host(mmg_index *idx);
 void mmg_index_free_device(mmg_index *idx);
+/* stream_host.cpp */
+void mmg_stream_shutdown(mmg_aligner *al);
 
 #endif

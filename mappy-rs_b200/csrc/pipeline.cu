@@ -402,6 +402,7 @@ int mmg_aligner_create_multi(const mmg_index *idx, const mmg_mapopt_t *mo, const
 void mmg_aligner_destroy(mmg_aligner *al)
 {
 	if (!al) return;
+	mmg_stream_shutdown(al);   /* stops the streaming worker (mmg_submit / mmg_next), if any */
 	if (!al->subs.empty()) {
 		for (size_t a = 0; a < al->subs.size(); ++a) mmg_aligner_destroy(al->subs[a]);
 		delete al;

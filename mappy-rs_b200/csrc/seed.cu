@@ -623,8 +623,8 @@ int launch_anchor_filter(const ChunkDev &c, const DevIndex &di, const DevOpt &o,
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
 	const size_t smem = (size_t)(2 * AF_TAB + AF_MAX_SEEDS + 1 + AF_MAX_ANCHORS / 32) * 4;
-	static bool attr_done = false;
-	if (!attr_done) { cudaFuncSetAttribute(anchor_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+	static unsigned char attr_done[64];
+	if (mmg_once_per_device(attr_done)) { cudaFuncSetAttribute(anchor_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
 	MMG_LAUNCH(anchor_filter_kernel, grid, AF_THREADS, smem, st, c, di, o, work);
 	return 0;
 }

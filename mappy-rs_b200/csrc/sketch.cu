@@ -284,8 +284,8 @@ static void launch_sketch_t(const ChunkDev &c, int w, int k, int grid, cudaStrea
 {
 	size_t smem = (size_t)SKETCH_WARPS * RING * (sizeof(KT) + 8) + (RING == 64 ? (size_t)SKETCH_WARPS * SK_LEVELS * RING * (sizeof(KT) + 4) : 0);
 	if (smem > 48 * 1024) {
-		static bool attr_done = false;
-		if (!attr_done) { cudaFuncSetAttribute(sketch_kernel<RING, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+		static unsigned char attr_done[64];
+		if (mmg_once_per_device(attr_done)) { cudaFuncSetAttribute(sketch_kernel<RING, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
 	}
 	MMG_LAUNCH((sketch_kernel<RING, KT>), grid, SKETCH_WARPS * 32, smem, st, c, w, k, work);
 }

@@ -306,8 +306,8 @@ int launch_sort(const ChunkDev &c, const DevIndex &di, uint32_t r0, uint32_t r1,
 	MMG_LAUNCH((sort_kernel<SORT_SMALL_ELEMS, false>), grid, SORT_THREADS, smem_small, st, c, r0, r1, work, c.big_list, work + 1, g_sort_small_max);
 	MMG_LAUNCH((radix_sort_kernel<false>), grid, RSORT_WARPS * 32, 0, st, c, di.seq_off, work + 2, (const uint32_t*)c.big_list, (const uint32_t*)(work + 1), c.tie_list, work + 3);
 	const size_t smem_tie = (size_t)RSORT_TIE_TILE * 12;
-	static bool attr_done = false;
-	if (!attr_done) { cudaFuncSetAttribute(radix_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tie); attr_done = true; }
+	static unsigned char attr_done[64];
+	if (mmg_once_per_device(attr_done)) { cudaFuncSetAttribute(radix_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tie); }
 	grid = n_sms * 2;
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;

@@ -60,7 +60,12 @@ EXPORTS = ["mmg_host_alloc", "mmg_host_free", "mmg_set_opt", "mmg_mapopt_update"
            "mmg_batch_upload", "mmg_batch_run", "mmg_batch_fetch", "mmg_batch_n_reads", "mmg_batch_n_hits",
            "mmg_batch_hit_off", "mmg_batch_hits", "mmg_batch_n_cigar", "mmg_batch_cigar", "mmg_gen_cs",
            "mmg_gen_md", "mmg_gen_tags", "mmg_debug_logf", "mmg_batch_destroy", "mmg_batch_stats", "mmg_stage_times", "mmg_stage_name",
-           "mmg_last_run_ms", "mmg_debug_dump", "mmg_last_error", "mmg_version", "mmg_sizeof_hit"]
+           "mmg_last_run_ms", "mmg_debug_dump", "mmg_last_error", "mmg_version", "mmg_sizeof_hit",
+           "mmg_submit", "mmg_flush", "mmg_next", "mmg_result_release"]
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("read_id", c_u64), ("n_hits", c_u32), ("hits", c_vp), ("cigar", c_vp), ("owner", c_vp)]
 
 
 class MmgError(RuntimeError):
@@ -117,6 +122,11 @@ class Lib:
         L.mmg_stage_name.restype = c_cp; L.mmg_stage_name.argtypes = [c_int]
         L.mmg_last_run_ms.restype = ctypes.c_double; L.mmg_last_run_ms.argtypes = [c_vp]
         L.mmg_debug_dump.restype = c_i64; L.mmg_debug_dump.argtypes = [c_vp, c_vp, c_int, c_vp, c_vp, c_u64, c_vp]
+        L.mmg_submit.argtypes = [c_vp, c_vp, c_vp, c_u32, c_u64]
+        L.mmg_flush.argtypes = [c_vp]
+        L.mmg_next.argtypes = [c_vp, P(Result), c_int]
+        L.mmg_result_release.argtypes = [c_vp, P(Result)]
+        L.mmg_result_release.restype = None
         L.mmg_last_error.restype = c_cp
         L.mmg_version.restype = c_cp
         assert L.mmg_sizeof_hit() == HIT_DTYPE.itemsize, (L.mmg_sizeof_hit(), HIT_DTYPE.itemsize)

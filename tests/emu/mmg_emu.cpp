@@ -21,8 +21,9 @@ cudaError_t cudaGetDeviceCount(int *n) { const char *e = getenv("MMG_EMU_DEVICES
 cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaMemcpyPeer(void *d, int, const void *s, int, size_t n) { memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static thread_local int emu_cur_dev = 0;
+cudaError_t cudaSetDevice(int d) { emu_cur_dev = d; return cudaSuccess; }
+cudaError_t cudaGetDevice(int *d) { *d = emu_cur_dev; return cudaSuccess; }
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { memset(p, 0, sizeof(*p)); const char *e = getenv("MMG_EMU_SMS"); p->multiProcessorCount = e ? atoi(e) : 4; p->totalGlobalMem = (size_t)8 << 30; p->sharedMemPerBlockOptin = 227 * 1024; strcpy(p->name, "mmg-emu"); p->major = 10; return cudaSuccess; }
 cudaError_t cudaMalloc(void **p, size_t n) { *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }

@@ -511,3 +511,57 @@ def test_unsupported_presets_are_rejected_not_approximated(emu_lib):
     emu_lib.check(emu_lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mo)))
     for preset in (b"sr", b"splice", b"map-pb", b"nonsense"):
         assert emu_lib.L.mmg_set_opt(preset, ctypes.byref(io), ctypes.byref(mo)) < 0
+
+
+def _stream_all(lib, aligner, buf, offs, pieces, hit_dtype):
+    """feeds the reads through mmg_submit in `pieces` calls, then collects every result with mmg_next"""
+    import ctypes
+    from mappy_rs import _mmg
+    n = len(offs) - 1
+    cuts = [n * k // pieces for k in range(pieces + 1)]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        o = np.ascontiguousarray(offs[a:b + 1])
+        lib.check(lib.L.mmg_submit(aligner.h, buf.ctypes.data, o.ctypes.data, b - a, a))
+    lib.check(lib.L.mmg_flush(aligner.h))
+    got = {}
+    res = _mmg.Result()
+    while True:
+        rc = lib.check(lib.L.mmg_next(aligner.h, ctypes.byref(res), 30000))
+        if rc == 0:
+            break
+        hits = _mmg.np_from(res.hits, res.n_hits, hit_dtype)
+        cig = [_mmg.np_from(res.cigar + 4 * int(h["cigar_off"]), int(h["n_cigar"]), np.uint32) for h in hits] if res.cigar else []
+        got[int(res.read_id)] = (hits, cig)
+        lib.L.mmg_result_release(aligner.h, ctypes.byref(res))
+    return got
+
+
+@pytest.mark.parametrize("cigar", [False, True])
+def test_submit_next_streaming_equals_map_batch(emu_lib, oracle_mod, cigar):
+    """mmg_submit / mmg_flush / mmg_next / mmg_result_release (the work queue + workers + result queue of
+    /root/reference/src/lib.rs:541-636, 972-991 behind the C ABI): every read comes back exactly once, with the hits
+    mmg_map_batch gives, whatever the submission granularity."""
+    from mappy_rs import _mmg
+    ref, coff, names, seqs = parity.random_reference(11, [150000, 60000])
+    c = parity.Case(emu_lib, names, seqs, cigar=cigar)
+    try:
+        buf, offs, _ = data_gen.make_reads(12, ref, coff, 40, 300, 3000)
+        want = c.aligner.map_batch(buf, offs)
+        for pieces in (1, 7):
+            got = _stream_all(emu_lib, c.aligner, buf, offs, pieces, _mmg.HIT_DTYPE)
+            assert sorted(got) == list(range(40))
+            for i in range(40):
+                w = want.read_hits(i)
+                h, cg = got[i]
+                assert len(h) == len(w)
+                for f in _mmg.HIT_DTYPE.names:
+                    if f != "cigar_off":
+                        assert np.array_equal(h[f], w[f]), (i, f)
+                for k in range(len(w)):
+                    if w["n_cigar"][k]:
+                        assert np.array_equal(cg[k], want.hit_cigar(w[k]))
+        import ctypes
+        res = _mmg.Result()
+        assert emu_lib.L.mmg_next(c.aligner.h, ctypes.byref(res), 10) == 0     # nothing outstanding
+    finally:
+        c.close()

@@ -110,3 +110,38 @@ def test_gpu_device_build_matches_reference_mmi(gpu_lib, tmp_path):
 def test_gpu_device_build_matches_host_and_oracle(gpu_lib, oracle_mod):
     _check_vs_host(gpu_lib, oracle_mod, None, [3000000, 700000, 9, 1200000], 7, 200)
     _check_vs_host(gpu_lib, oracle_mod, "map-hifi", [2000000, 300000], 8, 50)
+
+
+def test_gzip_fasta_fastq_and_multipart_mmi(emu_lib, tmp_path):
+    """mm_idx_reader_open reads FASTA / FASTQ, plain or gzip-compressed, and `Aligner` keeps only the FIRST part of a
+    multi-part .mmi (/root/reference/src/lib.rs:398-412)."""
+    import gzip
+    import shutil
+    io, _ = _opts(emu_lib)
+    gz = str(tmp_path / "test.fa.gz")
+    with open(FA, "rb") as f, gzip.open(gz, "wb") as g:
+        shutil.copyfileobj(f, g)
+    recs = []
+    for line in open(FA):
+        if line.startswith(">"):
+            recs.append([line[1:].strip(), ""])
+        else:
+            recs[-1][1] += line.strip()
+    fq = str(tmp_path / "test.fq.gz")
+    with gzip.open(fq, "wt") as g:
+        for n, s in recs:
+            g.write("@%s some description\n%s\n+\n%s\n" % (n, s, ">@+" * (len(s) // 3) + "I" * (len(s) % 3)))   # quality lines may start with > @ +
+    mmi2 = str(tmp_path / "two_parts.mmi")
+    with open(mmi2, "wb") as out:
+        blob = open(MMI, "rb").read()
+        out.write(blob + blob)
+    want = None
+    for path in (FA, gz, fq, MMI, mmi2):
+        ix = _mmg.Index.open(emu_lib, path, io)
+        try:
+            got = (_entries(ix), ix.n_seq, [ix.seq_name(i) for i in range(ix.n_seq)], [ix.seq_len(i) for i in range(ix.n_seq)])
+            if want is None:
+                want = got
+            assert got[1:] == want[1:] and np.array_equal(got[0][0], want[0][0]) and np.array_equal(got[0][1], want[0][1]), path
+        finally:
+            ix.close()
