@@ -105,6 +105,7 @@ WORKLOADS = {
     # name: (description, reference builder, read simulator kwargs, preset, reads per GPU default)
     "config1": "BASELINE.json configs[1]: 5 Mb synthetic reference (seed 1), simulated 1-10 kb ONT reads (3% sub, 2% ins, 3% del; seed 2), map-ont",
     "human": "BASELINE.json configs[2]: 3.1 Gb synthetic reference (24 contigs, GRCh38-proportional, seed 3), simulated 1-10 kb ONT reads (3% sub, 2% ins, 3% del; seed 4), map-ont, index replicated per GPU, reads sharded",
+    "human-repeats": "BASELINE.json configs[2] stress variant (SURVEY.md section 8d): the 3.1 Gb reference with 5 % planted repeat families (50 families x 1000 copies of 0.3-6 kb, 10 % divergence per copy), same reads, map-ont",
     "prefix": "BASELINE.json configs[3]: 400-base read prefixes streamed in batches of 20 000 (readfish-style), map-ont",
     "hifi": "BASELINE.json configs[4]: simulated HiFi reads N(15 kb, 2 kb) clipped to [10 kb, 25 kb], 0.5% errors (seed 5), map-hifi",
 }
@@ -113,9 +114,10 @@ WORKLOADS = {
 def workload(args, rank):
     """Returns (ref, coff, names, buf, offs, preset) for this rank's shard (weak scaling: args.reads per GPU)."""
     import data_gen
-    big = args.workload == "human" or args.ref == "human"
+    big = args.workload in ("human", "human-repeats") or args.ref == "human"
     if big:
-        ref, coff, names = data_gen.make_reference(3, data_gen.config2_contig_lens(args.ref_bases))
+        fam = dict(n_families=50, fam_copies=int(1000 * args.ref_bases / 3.1e9) or 1, rep_min=300, rep_max=6000, fam_div=0.1) if args.workload == "human-repeats" else {}
+        ref, coff, names = data_gen.make_reference(3, data_gen.config2_contig_lens(args.ref_bases), **fam)
     else:
         ref, coff, names = data_gen.config1_reference()
     seed = (4 if big else 2) + 1000 * rank
@@ -148,7 +150,7 @@ def make_oracle(args, ref, coff, names, preset, cigar):
 def config_of(args):
     """Static description of the workload: identical in the GPU arm and in `--impl reference`."""
     return {"workload": WORKLOADS[args.workload], "mode": "mapping-only" if args.mapping_only else "CIGAR on (MM_F_CIGAR, mappy-rs' only mode)",
-            "reads_per_gpu": args.reads, "ref": "3.1 Gb" if (args.workload == "human" or args.ref == "human") else "5 Mb",
+            "reads_per_gpu": args.reads, "ref": "3.1 Gb" if (args.workload in ("human", "human-repeats") or args.ref == "human") else "5 Mb",
             "parallelism": "reads sharded, index replicated", "l2": "inputs and per-chunk arenas are far larger than L2 (126 MB); no flush needed"}
 
 
@@ -310,7 +312,7 @@ def run_group(args, lib, io, mopt, idx, ref, coff, names, preset, hbuf, offs, ra
         al = _mmg.DeviceAligner(lib, gidx, m2, devices=list(range(world)))
         setup_s = time.perf_counter() - t0
         bufs, lens = [hbuf.numpy()], [np.diff(offs.astype(np.int64))]
-        big = args.workload == "human" or args.ref == "human"
+        big = args.workload in ("human", "human-repeats") or args.ref == "human"
         for r in range(1, world):   # the reads the other ranks mapped (same seeds)
             if args.workload == "hifi":
                 b, o, _ = data_gen.make_reads(5 + 1000 * r, ref, coff, args.reads, 10000, 25000, len_mean=15000.0, len_sd=2000.0, p_sub=0.002, p_ins=0.0015, p_del=0.0015)
@@ -500,7 +502,7 @@ def main():
     ap.add_argument("--no-group", action="store_true", help="N > 1: skip the one-process multi-device leg (one common batch sharded over all GPUs, gathered on rank 0)")
     args = ap.parse_args()
     if args.reads <= 0:
-        args.reads = {"config1": 200000, "human": 250000, "prefix": 400000, "hifi": 40000}[args.workload]
+        args.reads = {"config1": 200000, "human": 250000, "human-repeats": 250000, "prefix": 400000, "hifi": 40000}[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

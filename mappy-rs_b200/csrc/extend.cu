@@ -26,6 +26,8 @@
  * A region split by a z-drop creates a new region that is aligned in the next
  * round.  Bound: INT32 issue (DP cells), traceback bytes to HBM - see DESIGN.md.
  */
+#include <stdio.h>
+#include <stdlib.h>
 #include "dev_common.cuh"
 #include "dev_sort.cuh"
 #include "dev_regs.cuh"

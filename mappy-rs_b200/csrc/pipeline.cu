@@ -23,6 +23,19 @@
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { mmg_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return MMG_ECUDA; } } while (0)
 
+/* MMG_DEBUG_SYNC=1: synchronise after every stage and name the stage whose kernels faulted (fault isolation only) */
+static bool debug_sync() { static int v = -1; if (v < 0) v = getenv("MMG_DEBUG_SYNC") ? 1 : 0; return v == 1; }
+static void debug_check(const char *where, int device)
+{
+	if (!debug_sync()) return;
+	int cur = 0;
+	cudaGetDevice(&cur);
+	cudaSetDevice(device);
+	cudaError_t e = cudaDeviceSynchronize();
+	fprintf(stderr, "[mmg debug] %s: device %d: %s\n", where, device, cudaGetErrorString(e));
+	cudaSetDevice(cur);
+}
+
 static const char *g_stage_names[MMG_N_STAGES] = { "h2d", "sketch", "seed", "scan", "expand", "sort", "chain_dp", "backtrack", "rechain", "regs", "extend", "d2h" };
 
 /* Pinned host blocks that receive the hit records of streamed batches directly (no staging copy, no page faults on a
@@ -183,11 +196,18 @@ static int upload_index(mmg_aligner *al, const DevIndex *src = 0, int src_dev = 
 		int rc;
 		if ((rc = dev_alloc(al, &d_tab, nslots)) || (rc = dev_alloc(al, &d_pos, n_pos)) || (rc = dev_alloc(al, &d_S, n_S)) ||
 		    (rc = dev_alloc(al, &d_soff, idx->offs.size())) || (rc = dev_alloc(al, &d_slen, idx->lens.size()))) return rc;
-		int can = 0;
-		if (cudaDeviceCanAccessPeer(&can, al->device, src_dev) == cudaSuccess && can) { cudaDeviceEnablePeerAccess(src_dev, 0); cudaGetLastError(); }
+		/* peer access is switched on for the copies only (NVLink DMA instead of staging through the host) and off again:
+		 * nothing on the mapping path touches another device's memory */
+		int can = 0, enabled = 0;
+		if (cudaDeviceCanAccessPeer(&can, al->device, src_dev) == cudaSuccess && can) {
+			enabled = cudaDeviceEnablePeerAccess(src_dev, 0) == cudaSuccess;
+			cudaGetLastError();
+		}
 		CK(cudaMemcpyPeer(d_tab, al->device, src->htab, src_dev, nslots * sizeof(mmg_u128)));
 		if (n_pos) CK(cudaMemcpyPeer(d_pos, al->device, src->pos, src_dev, n_pos * 8));
 		if (n_S) CK(cudaMemcpyPeer(d_S, al->device, src->S, src_dev, n_S * 4));
+		CK(cudaDeviceSynchronize());   /* peer copies are asynchronous to the host, and the aligner's streams do not wait for the null stream */
+		if (enabled) { cudaDeviceDisablePeerAccess(src_dev); cudaGetLastError(); }
 		CK(cudaMemcpy(d_soff, idx->offs.data(), idx->offs.size() * 8, cudaMemcpyHostToDevice));
 		if (!idx->lens.empty()) CK(cudaMemcpy(d_slen, idx->lens.data(), idx->lens.size() * 4, cudaMemcpyHostToDevice));
 		di.htab = d_tab, di.pos = d_pos, di.S = d_S, di.seq_off = d_soff, di.seq_len = d_slen;
@@ -391,9 +411,15 @@ int mmg_aligner_create_multi(const mmg_index *idx, const mmg_mapopt_t *mo, const
 	int first = 0;
 	for (int a = 0; a < n_dev; ++a) if (devices[a] == idx->dev_device) first = a;
 	g->subs.assign(n_dev, (mmg_aligner*)0);
+	debug_check("create_multi: before", devices[first]);
 	int rc = aligner_create_on(idx, mo, devices[first], 0, -1, &g->subs[first]);
+	debug_check("create_multi: first member created", devices[first]);
 	for (int a = 0; a < n_dev && !rc; ++a)
-		if (a != first) rc = aligner_create_on(idx, mo, devices[a], &g->subs[first]->di, devices[first], &g->subs[a]);
+		if (a != first) {
+			rc = aligner_create_on(idx, mo, devices[a], &g->subs[first]->di, devices[first], &g->subs[a]);
+			debug_check("create_multi: member created (its device)", devices[a]);
+			debug_check("create_multi: member created (source device)", devices[first]);
+		}
 	if (rc) { mmg_aligner_destroy(g); return rc; }
 	*out = g;
 	return MMG_OK;
@@ -403,6 +429,7 @@ void mmg_aligner_destroy(mmg_aligner *al)
 {
 	if (!al) return;
 	mmg_stream_shutdown(al);   /* stops the streaming worker (mmg_submit / mmg_next), if any */
+	if (al->subs.empty()) debug_check("aligner_destroy: entry", al->device);
 	if (!al->subs.empty()) {
 		for (size_t a = 0; a < al->subs.size(); ++a) mmg_aligner_destroy(al->subs[a]);
 		delete al;
@@ -550,7 +577,9 @@ static void stage_collect(mmg_aligner *al)
 	al->ev_used = 0;
 }
 #define STAGE_BEGIN() do { if (al->profile) cudaEventRecord(stage_event(al, -1), st); } while (0)
-#define STAGE_END(id) do { al->stage_launches[id] += 1; if (al->profile) cudaEventRecord(stage_event(al, id), st); } while (0)
+#define STAGE_END(id) do { al->stage_launches[id] += 1; if (al->profile) cudaEventRecord(stage_event(al, id), st); \
+	if (debug_sync()) { cudaError_t e_ = cudaStreamSynchronize(st); if (e_ == cudaSuccess) e_ = cudaGetLastError(); \
+		if (e_ != cudaSuccess) { mmg_set_error("stage %s on device %d failed: %s (%s:%d)", g_stage_names[id], al->device, cudaGetErrorString(e_), __FILE__, __LINE__); return MMG_ECUDA; } } } while (0)
 
 /* Base-level alignment of the regions of reads [s0, s1): rounds of prep -> DP jobs -> stitch until no
  * region is left pending (a z-drop split creates a region that is aligned in the next round).  Within a round the
@@ -569,11 +598,14 @@ static int run_extension(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t s0
 		if (wi + EXT_DP_COUNTERS + 3 > 64) { CK(cudaMemsetAsync(c.work, 0, 64 * 4, st)); wi = 0; }
 		STAGE_BEGIN();
 		launch_ext_prep(c, al->di, al->dopt, xb, s0, s1, round, al->n_sms, st, work + wi++);
+		if (debug_sync()) { cudaError_t e_ = cudaStreamSynchronize(st); if (e_ != cudaSuccess) { mmg_set_error("ext_prep_kernel (round %d) on device %d failed: %s", round, al->device, cudaGetErrorString(e_)); return MMG_ECUDA; } }
 		al->h_ctl[0] = cg_end;   /* pinned: the CIGAR slices of this round's jobs start where the last round ended */
 		CK(cudaMemcpyAsync(xb.cg_base, al->h_ctl, 8, cudaMemcpyHostToDevice, st));
 		launch_ext_job_scan(xb, n_jobs_prev, st);
+		if (debug_sync()) { cudaError_t e_ = cudaStreamSynchronize(st); if (e_ != cudaSuccess) { mmg_set_error("ext_job_scan_kernel (round %d) on device %d failed: %s", round, al->device, cudaGetErrorString(e_)); return MMG_ECUDA; } }
 		CK(cudaMemsetAsync(xb.ovf_n, 0, 16, st));
-		launch_ext_dp(c, al->di, al->dopt, xb, n_jobs_prev, al->n_sms, st, work + wi); wi += EXT_DP_COUNTERS;
+		if (launch_ext_dp(c, al->di, al->dopt, xb, n_jobs_prev, al->n_sms, st, work + wi)) { mmg_set_error("a DP kernel faulted (round %d, device %d): see stderr", round, al->device); return MMG_ECUDA; }
+		wi += EXT_DP_COUNTERS;
 		CK(cudaMemsetAsync(xb.n_pending, 0, 4, st));
 		launch_ext_stitch(c, al->di, al->dopt, xb, s0, s1, round, al->n_sms, st, work + wi++);
 		CK(cudaMemcpyAsync(al->h_ctl + 1, xb.cg_base + 1, 8, cudaMemcpyDeviceToHost, st));

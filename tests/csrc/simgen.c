@@ -39,6 +39,31 @@ void sim_plant_repeats(uint64_t seed, char *ref, uint64_t len, int n_rep, int lm
 	}
 }
 
+/* Repeat FAMILIES (SURVEY.md section 8d stress variant): n_fam random consensus sequences of lmin..lmax bases, each
+ * copied `copies` times to random places with per-base divergence dv - high-copy k-mers that exercise
+ * mm_seed_select / mid_occ, equal anchor keys and the re-chaining path. */
+void sim_plant_families(uint64_t seed, char *ref, uint64_t len, int n_fam, int copies, int lmin, int lmax, double dv)
+{
+	uint64_t s = seed * 0x9E3779B97F4A7C15ULL + 11;
+	char *cons = (char*)malloc((size_t)lmax + 1);
+	for (int f = 0; f < n_fam; ++f) {
+		uint64_t l = lmin + sm64(&s) % (uint64_t)(lmax - lmin + 1);
+		if (l * 2 >= len) continue;
+		for (uint64_t i = 0; i < l; ++i) cons[i] = "ACGT"[sm64(&s) & 3];
+		for (int c = 0; c < copies; ++c) {
+			uint64_t dst = sm64(&s) % (len - l);
+			int rev = (int)(sm64(&s) & 1);
+			for (uint64_t i = 0; i < l; ++i) {
+				char b = rev ? cons[l - 1 - i] : cons[i];
+				if (rev) b = b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : 'A';
+				if (u01(&s) < dv) b = "ACGT"[sm64(&s) & 3];
+				ref[dst + i] = b;
+			}
+		}
+	}
+	free(cons);
+}
+
 static inline char comp(char c) { switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return c; } }
 
 /* Simulate reads from a concatenated reference with contig table (coff[n_ctg+1]).

@@ -27,6 +27,7 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(build())
         _lib.sim_reference.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+        _lib.sim_plant_families.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
         _lib.sim_plant_repeats.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_double]
         _lib.sim_reads.restype = ctypes.c_uint64
@@ -37,8 +38,9 @@ def lib():
     return _lib
 
 
-def make_reference(seed, contig_lens, n_repeats=0, rep_min=300, rep_max=6000, rep_div=0.05):
-    """Returns (ref uint8 array of ASCII bases, contig offsets uint64[n+1], names)."""
+def make_reference(seed, contig_lens, n_repeats=0, rep_min=300, rep_max=6000, rep_div=0.05, n_families=0, fam_copies=0, fam_div=0.1):
+    """Returns (ref uint8 array of ASCII bases, contig offsets uint64[n+1], names).  n_repeats: two-copy duplications;
+    n_families x fam_copies: high-copy repeat families (consensus of rep_min..rep_max bases, fam_div divergence per copy)."""
     contig_lens = [int(x) for x in contig_lens]
     coff = np.zeros(len(contig_lens) + 1, dtype=np.uint64)
     coff[1:] = np.cumsum(contig_lens)
@@ -47,6 +49,8 @@ def make_reference(seed, contig_lens, n_repeats=0, rep_min=300, rep_max=6000, re
     lib().sim_reference(seed, total, ref.ctypes.data)
     if n_repeats:
         lib().sim_plant_repeats(seed + 1000, ref.ctypes.data, total, n_repeats, rep_min, rep_max, rep_div)
+    if n_families and fam_copies:
+        lib().sim_plant_families(seed + 2000, ref.ctypes.data, total, n_families, fam_copies, rep_min, rep_max, fam_div)
     names = ["chr%d" % (i + 1) for i in range(len(contig_lens))]
     return ref, coff, names
 

@@ -20,6 +20,7 @@ static const char *emu_err = "no error";
 cudaError_t cudaGetDeviceCount(int *n) { const char *e = getenv("MMG_EMU_DEVICES"); *n = e ? atoi(e) : 1; return cudaSuccess; }
 cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+cudaError_t cudaDeviceDisablePeerAccess(int) { return cudaSuccess; }
 cudaError_t cudaMemcpyPeer(void *d, int, const void *s, int, size_t n) { memmove(d, s, n); return cudaSuccess; }
 static thread_local int emu_cur_dev = 0;
 cudaError_t cudaSetDevice(int d) { emu_cur_dev = d; return cudaSuccess; }

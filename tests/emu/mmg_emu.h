@@ -48,6 +48,7 @@ cudaError_t cudaGetDeviceCount(int *n);
 cudaError_t cudaSetDevice(int d);
 cudaError_t cudaDeviceCanAccessPeer(int *can, int dev, int peer);
 cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned flags);
+cudaError_t cudaDeviceDisablePeerAccess(int peer);
 cudaError_t cudaMemcpyPeer(void *d, int ddev, const void *s, int sdev, size_t n);
 cudaError_t cudaGetDevice(int *d);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int d);
