@@ -54,7 +54,7 @@ struct ExtBufs {
 
 int launch_ext_prep(const ChunkDev &c, const DevIndex &di, const DevOpt &o, const ExtBufs &xb, uint32_t r0, uint32_t r1, int round, int n_sms, cudaStream_t st, uint32_t *work);
 /* j1 is read from the device (*xb.n_jobs) by these two: no host round trip between prep, scan, DP and stitch */
-int launch_ext_job_scan(const ExtBufs &xb, uint32_t j0, cudaStream_t st);
+int launch_ext_job_scan(const ExtBufs &xb, uint32_t j0, int n_sms, cudaStream_t st);
 int launch_ext_dp(const ChunkDev &c, const DevIndex &di, const DevOpt &o, const ExtBufs &xb, uint32_t j0, int n_sms, cudaStream_t st, uint32_t *work);
 #define EXT_DP_COUNTERS 6   /* claim counters launch_ext_dp uses */
 int launch_ext_stitch(const ChunkDev &c, const DevIndex &di, const DevOpt &o, const ExtBufs &xb, uint32_t r0, uint32_t r1, int round, int n_sms, cudaStream_t st, uint32_t *work);

@@ -340,6 +340,18 @@ static int aligner_create_on(const mmg_index *idx, const mmg_mapopt_t *mo, int d
 	const int64_t unsup = 0x80LL | 0x100LL | 0x200LL | 0x1000LL | 0x2000LL | MMG_F_FOR_ONLY | MMG_F_REV_ONLY | 0x400000LL | 0x20000000LL | 0x100000000LL;
 	if (mo->flag & unsup) { mmg_set_error("mapping flag 0x%llx selects a code path outside the supported long-read path", (unsigned long long)(mo->flag & unsup)); return MMG_EUNSUP; }
 	if (idx->flag & MMG_I_HPC) { mmg_set_error("homopolymer-compressed indexes are not supported"); return MMG_EUNSUP; }
+	if (mo->flag & MMG_F_CIGAR) {
+		/* the limits inside which ksw_extd2_sse / ksw_extz2_sse compute what they are meant to: their 8-bit lanes wrap beyond
+		 * (q+e)+(q2+e2) <= 127 (minimap2's mm_check_opt states this one; mappy-rs does not call it, src/lib.rs:339-385),
+		 * and both kernels return without a result when a substitution costs more than 2*(q+e).  Outside them upstream's
+		 * output is an artefact of the wrap-around, so such scorings are refused instead of reproduced. */
+		if (mo->transition != 0 && mo->transition != mo->b) { mmg_set_error("a separate transition score is not supported (mappy-rs cannot set one)"); return MMG_EUNSUP; }
+		const int qe = mo->q + mo->e, qe2 = mo->q2 + mo->e2, worst = std::max(std::max(mo->b, mo->sc_ambi), mo->transition);
+		if (mo->a < 1 || mo->b < 0 || mo->q < 0 || mo->e < 1 || mo->q2 < 0 || mo->e2 < 1 || mo->sc_ambi < 0 || mo->transition < 0) {
+			mmg_set_error("scoring: a, e, e2 must be positive and b, q, q2, sc_ambi, transition non-negative"); return MMG_EINVAL; }
+		if (qe + qe2 > 127 || mo->a + std::max(qe, qe2) > 127) { mmg_set_error("scoring system violates (O1+E1)+(O2+E2) <= 127 and A+max(O+E) <= 127: minimap2's 8-bit DP lanes wrap beyond it"); return MMG_EINVAL; }
+		if (worst > 2 * qe) { mmg_set_error("scoring: a mismatch / ambiguous-base penalty above 2*(O1+E1) makes minimap2's DP kernels return no alignment"); return MMG_EINVAL; }
+	}
 	if (idx->offs.back() >= ((uint64_t)1 << 35)) { mmg_set_error("references of 2^35 bases or more are not supported"); return MMG_EUNSUP; }
 	CK(cudaSetDevice(device));
 #define CKA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { mmg_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); mmg_aligner_destroy(al); return MMG_ECUDA; } } while (0)
@@ -365,10 +377,11 @@ static int aligner_create_on(const mmg_index *idx, const mmg_mapopt_t *mo, int d
 	al->profile = 0;
 	al->cap_bases = (uint64_t)96 << 20, al->cap_reads = 1u << 17, al->cap_anchors = (uint64_t)48 << 20, al->cap_regs = (uint64_t)4 << 20;
 	al->cap_keep_words = (uint64_t)1 << 22; /* unfiltered anchors per chunk the isolated-anchor filter can look at: 2^27, 2^29 on a 180 GB device */
-	if (prop.totalGlobalMem >= ((size_t)120 << 30) && !(mo->flag & MMG_F_CIGAR)) {
-		/* B200 (180 GB): mapping-only chunks of 384 Mbases / 256 M anchors (~60 GB of arenas).  Every stage kernel
-		 * ends with a tail of a few long-running reads (long reads, equal-key replays); fewer, larger chunks pay
-		 * that tail fewer times per batch. */
+	if (prop.totalGlobalMem >= ((size_t)120 << 30)) {
+		/* B200 (180 GB): chunks of 384 Mbases / 256 M anchors (~60 GB of arenas; with CIGAR + 32 GB of traceback slices
+		 * and 5 GB of CIGAR arena).  Every stage kernel ends with a tail of a few long-running reads (long reads,
+		 * equal-key replays, the last batches of the DP kernels); fewer, larger chunks pay that tail fewer times per
+		 * batch: configs[2] with CIGAR 225 k -> 246 k reads/s against 96-Mbase chunks. */
 		al->cap_bases = (uint64_t)384 << 20, al->cap_reads = 1u << 19, al->cap_anchors = (uint64_t)256 << 20, al->cap_regs = (uint64_t)16 << 20;
 		al->cap_keep_words = (uint64_t)1 << 24;
 	}
@@ -503,6 +516,7 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 	else if (strcmp(key, "chunk_reads") == 0) al->cap_reads = (uint32_t)v;
 	else if (strcmp(key, "anchor_cap") == 0) al->cap_anchors = (uint64_t)v;
 	else if (strcmp(key, "regs_cap") == 0) al->cap_regs = (uint64_t)v;
+	else if (strcmp(key, "keep_words") == 0) al->cap_keep_words = (uint64_t)v;
 	else if (strcmp(key, "tb_cap") == 0) al->cap_tb = (uint64_t)v;
 	else if (strcmp(key, "cigar_cap") == 0) al->cap_cg = (uint64_t)v;
 	else if (strcmp(key, "jobs_cap") == 0) al->cap_jobs = (uint64_t)v;
@@ -599,9 +613,9 @@ static int run_extension(mmg_aligner *al, mmg_batch *b, ChunkDev &c, uint32_t s0
 		STAGE_BEGIN();
 		launch_ext_prep(c, al->di, al->dopt, xb, s0, s1, round, al->n_sms, st, work + wi++);
 		if (debug_sync()) { cudaError_t e_ = cudaStreamSynchronize(st); if (e_ != cudaSuccess) { mmg_set_error("ext_prep_kernel (round %d) on device %d failed: %s", round, al->device, cudaGetErrorString(e_)); return MMG_ECUDA; } }
-		al->h_ctl[0] = cg_end;   /* pinned: the CIGAR slices of this round's jobs start where the last round ended */
-		CK(cudaMemcpyAsync(xb.cg_base, al->h_ctl, 8, cudaMemcpyHostToDevice, st));
-		launch_ext_job_scan(xb, n_jobs_prev, st);
+		al->h_ctl[0] = al->h_ctl[1] = cg_end;   /* pinned: the CIGAR slices of this round's jobs start where the last round ended; [1] becomes the new end */
+		CK(cudaMemcpyAsync(xb.cg_base, al->h_ctl, 16, cudaMemcpyHostToDevice, st));
+		launch_ext_job_scan(xb, n_jobs_prev, al->n_sms, st);
 		if (debug_sync()) { cudaError_t e_ = cudaStreamSynchronize(st); if (e_ != cudaSuccess) { mmg_set_error("ext_job_scan_kernel (round %d) on device %d failed: %s", round, al->device, cudaGetErrorString(e_)); return MMG_ECUDA; } }
 		CK(cudaMemsetAsync(xb.ovf_n, 0, 16, st));
 		if (launch_ext_dp(c, al->di, al->dopt, xb, n_jobs_prev, al->n_sms, st, work + wi)) { mmg_set_error("a DP kernel faulted (round %d, device %d): see stderr", round, al->device); return MMG_ECUDA; }

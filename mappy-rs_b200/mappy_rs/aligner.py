@@ -22,6 +22,10 @@ import numpy as np
 
 from . import _mmg
 
+_utf8_and_size = ctypes.pythonapi.PyUnicode_AsUTF8AndSize     # a str's UTF-8 bytes in place (ASCII: the str's own buffer)
+_utf8_and_size.restype = ctypes.c_void_p
+_utf8_and_size.argtypes = [ctypes.py_object, ctypes.POINTER(ctypes.c_ssize_t)]
+_STR_ONLY = frozenset((str,))
 _WORK_QUEUE_CAP = 50000   # lib.rs:429-430
 _DRAIN_BASES = 32 << 20   # the worker starts a device batch as soon as this many bases are queued ...
 _IDLE_S = 0.02            # ... or the producer has pushed nothing for this long (a slow generator still streams)
@@ -143,6 +147,10 @@ class AlignmentBatchResultIter:
         return self
 
     def __next__(self):
+        try:
+            return self._q.popleft()       # deque.popleft is atomic: no lock while results are waiting
+        except IndexError:
+            pass
         with self._cv:
             while not self._q and not self._finished:
                 self._cv.wait(0.05)
@@ -240,18 +248,31 @@ class Aligner:
     # ---- mapping ----------------------------------------------------------------------
     def _map_reads(self, seqs, cs, md):
         """list[str] -> per-read lists of Mapping, through mmg_map_batch (host buffers in, results out)."""
-        bs = [s.encode() for s in seqs]
-        offs = np.zeros(len(bs) + 1, dtype=np.uint64)
-        offs[1:] = np.cumsum([len(b) for b in bs])
+        n = len(seqs)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        # ASCII reads (every real one): one join, then one copy out of the str's own buffer straight into the pinned block
+        # (ctypes releases the GIL for it); anything else goes through encode() and is sized by its UTF-8 bytes
+        joined = "".join(seqs)
+        size = ctypes.c_ssize_t(0)
+        src = _utf8_and_size(joined, ctypes.byref(size))
+        if size.value == len(joined):
+            np.cumsum(np.fromiter(map(len, seqs), dtype=np.uint64, count=n), out=offs[1:])
+            bs = None
+        else:
+            bs = [s.encode() for s in seqs]
+            np.cumsum(np.fromiter(map(len, bs), dtype=np.uint64, count=n), out=offs[1:])
         with self._lock:
             # the reads are assembled in page-locked memory: the library's chunked host->device copies then overlap its kernels
             buf = self._pinned.view(int(offs[-1]))
             if offs[-1]:
-                buf[:] = np.frombuffer(b"".join(bs), dtype=np.uint8)
+                if bs is None:
+                    ctypes.memmove(buf.ctypes.data, src, size.value)
+                else:
+                    buf[:] = np.frombuffer(b"".join(bs), dtype=np.uint8)
             res = self._aligner.map_batch(buf, offs)
             cs_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 0) if cs else None   # reads the shared pinned buffer
             md_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 1) if md else None
-        return _mappings_of_batch(res, self._names, self._lens, cs_l, md_l, len(bs))
+        return _mappings_of_batch(res, self._names, self._lens, cs_l, md_l, n)
 
     def map(self, seq, seq2=None, cs=False, MD=False):
         """Map a single read, blocking (lib.rs:472-514)."""
@@ -301,8 +322,12 @@ class Aligner:
                             cv.wait(_IDLE_S / 2 if n else 0.05)
                         if state["abort"]:   # the producer raised: nothing is returned to the caller (lib.rs:847-866 return early)
                             break
-                        items = list(work)
-                        work.clear()
+                        items = []
+                        try:                       # item by item: the producer appends without the lock
+                            while True:
+                                items.append(work.popleft())
+                        except IndexError:
+                            pass
                         state["bases"] = 0
                         done = state["done"]
                         cv.notify_all()
@@ -321,7 +346,7 @@ class Aligner:
         ok = False
         try:
             for id_num, item in enumerate(iter(seqs)):
-                if not isinstance(item, dict) or not all(isinstance(k_, str) for k_ in item):
+                if not isinstance(item, dict) or not _STR_ONLY.issuperset(map(type, item)) and not all(isinstance(k_, str) for k_ in item):
                     raise TypeError("Element in iterable is not a dictionary")
                 data = dict(item)                      # lib.rs:847-855: a new dict with the same keys / values
                 if "seq" not in item:
@@ -329,6 +354,13 @@ class Aligner:
                 seq = item["seq"]
                 if not isinstance(seq, str):
                     raise ValueError("`seq` must be a string")
+                if len(work) < _WORK_QUEUE_CAP - 1 and state["bases"] + len(seq) < _DRAIN_BASES:
+                    # the common case takes no lock: deque.append is atomic, `bases` has one writer while the queue fills,
+                    # and the worker wakes on its own timer if a notify is missed
+                    work.append((data, seq))
+                    state["bases"] += len(seq)
+                    state["last_push"] = time.monotonic()
+                    continue
                 with cv:
                     if len(work) >= _WORK_QUEUE_CAP:
                         if not back_off:

@@ -12,12 +12,21 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 def main():
     rep = sys.argv[1]
     tag = sys.argv[2] if len(sys.argv) > 2 else ""
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):   # the raw-page export of a report
+        txt = "".join(l for l in open(rep) if not l.startswith("=="))
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     h, units = rows[0], rows[1]
     kn, rd, wr, du = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
     per = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    n_chunks = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # stage launches (chunks) the capture covers
+    seen_sketch = 0
     for r in rows[2:]:
+        if "sketch_kernel" in r[kn]:      # a chunk starts with its sketch: stop after the chunks asked for
+            seen_sketch += 1
+            if seen_sketch > n_chunks:
+                break
         st = next((s for k, s in STAGE if k in r[kn]), None)
         if st is None:
             continue
@@ -25,7 +34,6 @@ def main():
         per[st][0] += 1
         per[st][1] += b
         per[st][2] += float(r[du].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[du], 1.0)
-    n_chunks = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # stage launches (chunks) the capture covers
     out = {st: {"dram_bytes_per_launch": v[1] / n_chunks, "kernels_captured": v[0], "stage_launches_captured": n_chunks, "ms_under_ncu_per_launch": v[2] / n_chunks,
                 "report": os.path.basename(rep), "workload": tag} for st, v in per.items()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise ncu outputs brought back in gpurun_out/ into profiles/ (tracked).
-usage: summarize.py <tag> [launches.csv] [prof_a.ncu-rep prof_b.ncu-rep ...]"""
+usage: summarize.py <tag> [launches.csv] [prof_a.ncu-rep | prof_a_raw.csv ...]"""
 import collections
 import csv
 import subprocess
@@ -38,7 +38,11 @@ def launches(path, out):
 
 
 def report(path, out):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """a .ncu-rep, or the `ncu -i rep --page raw --csv` export of one (what travels back from the GPU box)"""
+    if path.endswith(".csv"):
+        txt = "".join(l for l in open(path) if not l.startswith("=="))
+    else:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     h, units = rows[0], rows[1]
     for v in rows[2:]:
@@ -53,5 +57,5 @@ if __name__ == "__main__":
     tag = sys.argv[1]
     with open("profiles/%s.txt" % tag, "w") as out:
         for a in sys.argv[2:]:
-            (launches if a.endswith(".csv") else report)(a, out)
+            (launches if a.endswith(".csv") and not a.endswith("_raw.csv") else report)(a, out)
     print(open("profiles/%s.txt" % tag).read())

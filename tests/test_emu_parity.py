@@ -513,6 +513,25 @@ def test_unsupported_presets_are_rejected_not_approximated(emu_lib):
         assert emu_lib.L.mmg_set_opt(preset, ctypes.byref(io), ctypes.byref(mo)) < 0
 
 
+def test_scorings_outside_minimap2s_8bit_range_are_refused(emu_lib):
+    """ksw_extd2_sse wraps beyond (O1+E1)+(O2+E2) <= 127 and returns nothing when b > 2*(O1+E1): such a scoring=
+    (src/lib.rs:360-381) is refused at aligner creation, not answered with something else"""
+    import ctypes
+    from mappy_rs import _mmg
+    idx = None
+    for a, b, q, e, q2, e2 in ((2, 4, 60, 10, 60, 9), (2, 30, 4, 2, 24, 1), (120, 4, 4, 2, 24, 1), (0, 4, 4, 2, 24, 1)):
+        io, mo = _mmg.IdxOpt(), _mmg.MapOpt()
+        emu_lib.check(emu_lib.L.mmg_set_opt(None, ctypes.byref(io), ctypes.byref(mo)))
+        idx = idx or _mmg.Index.open(emu_lib, MMI, io)
+        emu_lib.check(emu_lib.L.mmg_mapopt_update(ctypes.byref(mo), idx.h))
+        mo.flag |= 4
+        mo.a, mo.b, mo.q, mo.e, mo.q2, mo.e2 = a, b, q, e, q2, e2
+        with pytest.raises(RuntimeError, match="scoring"):
+            _mmg.DeviceAligner(emu_lib, idx, mo)
+        mo.flag &= ~4       # without CIGAR no DP kernel runs: chaining does not look at the scoring
+        _mmg.DeviceAligner(emu_lib, idx, mo).close()
+
+
 def _stream_all(lib, aligner, buf, offs, pieces, hit_dtype):
     """feeds the reads through mmg_submit in `pieces` calls, then collects every result with mmg_next"""
     import ctypes
