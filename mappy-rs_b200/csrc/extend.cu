@@ -493,9 +493,10 @@ __device__ __forceinline__ uint32_t ext_n_jobs(const ExtBufs &xb)
 /* true when the CIGAR slices of the queued jobs fit the arena (else DP and stitch do nothing and the host reports it) */
 __device__ __forceinline__ bool ext_cigar_fits(const ExtBufs &xb) { return xb.cg_base[1] <= xb.cap_cg; }
 
-/* CIGAR slices of jobs [j0, *n_jobs): every block sums the sizes of 1024 jobs and claims that much of the arena with
- * one atomic (cg_base[1] enters as the round's base and leaves as its end).  Which slice a job gets is of no
- * consequence - ext_stitch copies the operations out by job - so no ordered scan over all jobs is needed. */
+/* exclusive scan of the per-job cigar sizes of jobs [j0, *n_jobs) (single block, 8 consecutive jobs per thread).
+ * The scan must be the ordered one: ext_stitch builds a region's CIGAR in place over the contiguous slices of the
+ * region's consecutive jobs. */
+#define JOB_SCAN_PER 8
 __global__ void __launch_bounds__(1024)
 ext_job_scan_kernel(ExtBufs xb, uint32_t j0)
 {
@@ -503,9 +504,15 @@ ext_job_scan_kernel(ExtBufs xb, uint32_t j0)
 	__shared__ unsigned long long s_cb;
 	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
 	const uint32_t j1 = ext_n_jobs(xb);
-	for (uint64_t i0 = (uint64_t)j0 + (uint64_t)blockIdx.x * 1024; i0 < j1; i0 += (uint64_t)gridDim.x * 1024) {
-		const uint64_t i = i0 + threadIdx.x;
-		unsigned long long vb = i < j1 ? xb.jobs[i].cg_size : 0, xbv = vb;
+	if (threadIdx.x == 0) s_cb = xb.cg_base[0];
+	__syncthreads();
+	for (uint64_t i0 = j0; i0 < j1; i0 += 1024 * JOB_SCAN_PER) {
+		const uint64_t i = i0 + (uint64_t)threadIdx.x * JOB_SCAN_PER;
+		uint32_t sz[JOB_SCAN_PER];
+		unsigned long long vb = 0;
+#pragma unroll
+		for (int k = 0; k < JOB_SCAN_PER; ++k) sz[k] = i + k < j1 ? xb.jobs[i + k].cg_size : 0u, vb += sz[k];
+		unsigned long long xbv = vb;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			unsigned long long yb = __shfl_up_sync(MMG_FULL, xbv, d);
@@ -521,12 +528,18 @@ ext_job_scan_kernel(ExtBufs xb, uint32_t j0)
 				if (lane >= d) sb += yb;
 			}
 			s_b[lane] = sb - wb;
-			if (lane == 31) s_cb = atomicAdd(&xb.cg_base[1], sb);
 		}
 		__syncthreads();
-		if (i < j1) xb.jobs[i].tb_off = 0, xb.jobs[i].cg_off = s_cb + s_b[wib] + xbv - vb;
+		const unsigned long long cb = s_cb;
+		unsigned long long at = cb + s_b[wib] + xbv - vb;
+#pragma unroll
+		for (int k = 0; k < JOB_SCAN_PER; ++k)
+			if (i + k < j1) xb.jobs[i + k].tb_off = 0, xb.jobs[i + k].cg_off = at, at += sz[k];
+		__syncthreads();
+		if (threadIdx.x == 1023) s_cb = cb + s_b[wib] + xbv;
 		__syncthreads();
 	}
+	if (threadIdx.x == 0) xb.cg_base[1] = s_cb;
 }
 
 /* ---------- the DP ---------- */
