@@ -493,21 +493,24 @@ __device__ __forceinline__ uint32_t ext_n_jobs(const ExtBufs &xb)
 /* true when the CIGAR slices of the queued jobs fit the arena (else DP and stitch do nothing and the host reports it) */
 __device__ __forceinline__ bool ext_cigar_fits(const ExtBufs &xb) { return xb.cg_base[1] <= xb.cap_cg; }
 
-/* exclusive scan of the per-job cigar sizes of jobs [j0, *n_jobs) (single block, 8 consecutive jobs per thread).
- * The scan must be the ordered one: ext_stitch builds a region's CIGAR in place over the contiguous slices of the
- * region's consecutive jobs. */
+/* Exclusive scan of the per-job cigar sizes of jobs [j0, *n_jobs).  It must be the ordered scan: ext_stitch builds a
+ * region's CIGAR in place over the contiguous slices of the region's consecutive jobs.  Chained over tiles of 8192 jobs:
+ * block b takes tiles b, b + grid, ...; a tile adds its sum to the inclusive prefix its predecessor publishes in
+ * `chain` (value << 1 | ready; zeroed by the host).  Every block is resident (one per SM) and takes its tiles in
+ * increasing order, so the tile a block waits for is always owned by a block that is not waiting on a later one. */
 #define JOB_SCAN_PER 8
+#define JOB_SCAN_TILE (1024 * JOB_SCAN_PER)
 __global__ void __launch_bounds__(1024)
-ext_job_scan_kernel(ExtBufs xb, uint32_t j0)
+ext_job_scan_kernel(ExtBufs xb, uint32_t j0, unsigned long long *chain)
 {
 	__shared__ unsigned long long s_b[32];
 	__shared__ unsigned long long s_cb;
 	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
 	const uint32_t j1 = ext_n_jobs(xb);
-	if (threadIdx.x == 0) s_cb = xb.cg_base[0];
-	__syncthreads();
-	for (uint64_t i0 = j0; i0 < j1; i0 += 1024 * JOB_SCAN_PER) {
-		const uint64_t i = i0 + (uint64_t)threadIdx.x * JOB_SCAN_PER;
+	if (j1 <= j0) { if (blockIdx.x == 0 && threadIdx.x == 0) xb.cg_base[1] = xb.cg_base[0]; return; }
+	const uint32_t n_tiles = (j1 - j0 + JOB_SCAN_TILE - 1) / JOB_SCAN_TILE;
+	for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const uint64_t i = (uint64_t)j0 + (uint64_t)tile * JOB_SCAN_TILE + (uint64_t)threadIdx.x * JOB_SCAN_PER;
 		uint32_t sz[JOB_SCAN_PER];
 		unsigned long long vb = 0;
 #pragma unroll
@@ -528,18 +531,32 @@ ext_job_scan_kernel(ExtBufs xb, uint32_t j0)
 				if (lane >= d) sb += yb;
 			}
 			s_b[lane] = sb - wb;
+			if (lane == 31) { /* sb = the tile's sum */
+				unsigned long long before;
+				if (tile == 0) before = xb.cg_base[0];
+				else {
+					volatile unsigned long long *prev = chain + (tile - 1);
+					unsigned long long v;
+					while (!((v = *prev) & 1ull)) {
+#ifndef MMG_EMU
+						__nanosleep(64);
+#endif
+					}
+					before = v >> 1;
+				}
+				s_cb = before;
+				__threadfence();
+				*(volatile unsigned long long*)(chain + tile) = (before + sb) << 1 | 1ull;
+				if (tile == n_tiles - 1) xb.cg_base[1] = before + sb;
+			}
 		}
 		__syncthreads();
-		const unsigned long long cb = s_cb;
-		unsigned long long at = cb + s_b[wib] + xbv - vb;
+		unsigned long long at = s_cb + s_b[wib] + xbv - vb;
 #pragma unroll
 		for (int k = 0; k < JOB_SCAN_PER; ++k)
 			if (i + k < j1) xb.jobs[i + k].tb_off = 0, xb.jobs[i + k].cg_off = at, at += sz[k];
 		__syncthreads();
-		if (threadIdx.x == 1023) s_cb = cb + s_b[wib] + xbv;
-		__syncthreads();
 	}
-	if (threadIdx.x == 0) xb.cg_base[1] = s_cb;
 }
 
 /* ---------- the DP ---------- */

@@ -277,7 +277,7 @@ static int alloc_arenas(mmg_aligner *al)
 		x.cap_jobs = al->cap_jobs, x.cap_tb = al->cap_tb, x.cap_cg = al->cap_cg, x.big_per_warp = al->big_per_warp;
 		AL(x.jobs, x.cap_jobs); AL(x.n_jobs, 4); AL(x.xregs, G); AL(x.regs_tmp, G); AL(x.n_sq, R);
 		AL(x.tb, x.cap_tb + 64); AL(x.jcigar, x.cap_cg); AL(x.rcigar, x.cap_cg);
-		AL(x.tb_base, 2); AL(x.cg_base, 2); AL(x.n_pending, 4); AL(x.reg_cap, R); AL(x.ovf, x.cap_jobs); AL(x.ovf_n, 4);
+		AL(x.tb_base, 2); AL(x.cg_base, 2); AL(x.n_pending, 4); AL(x.reg_cap, R); AL(x.ovf, x.cap_jobs + 16); AL(x.ovf_n, 4);
 		AL(x.big, (uint64_t)al->n_sms * 32 * x.big_per_warp); /* one slice per resident warp of the prep (8x4 per SM) and DP (4x4 per SM) grids */
 		AL(al->cg_read_off, R + 1);
 		x.xr_off = c.r_off;
