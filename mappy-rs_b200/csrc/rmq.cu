@@ -14,6 +14,7 @@
  * walks it while the warp handles the data-parallel parts (sort detection,
  * backtrack copy loops).
  */
+#include <stdlib.h>
 #include "dev_common.cuh"
 #include "dev_sort.cuh"
 #include "dev_chain.cuh"
@@ -390,8 +391,144 @@ __device__ void dev_lchain_rmq(int max_dist, int max_dist_inner, int bw, int max
 #undef RN_FREE
 }
 
+/* mm_lchain_rmq with the OUTER tree replaced by what it stands for.  The outer tree only ever holds the anchors
+ * [st, i0) - inserted when the target position moves on, erased from the front - so its range-minimum query is a scan
+ * of that index range for the smallest priority among the anchors whose query position lies in the interval: 32 anchors
+ * per step and a warp reduction instead of ~30 dependent node visits.  The tree matters in one case only: when the
+ * minimum is attained twice, krmq's answer depends on the shape of the tree.  Then the function gives up (returns 1)
+ * and the caller replays the read with the tree (dev_lchain_rmq).  The inner tree (anchors within max_dist_inner, walked
+ * in key order with the n_skip / t[] logic) is kept as it is, on lane 0.  Priorities are compared as order-preserving
+ * 64-bit keys of the very doubles upstream computes. */
+__device__ int dev_lchain_rmq_warp(int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, float pen_gap, float pen_skip,
+                                   int n, const uint64_t *ax, const uint64_t *ay, int32_t *f, int32_t *p, int32_t *t, RNode *nodes, unsigned long long *pk)
+{
+	const int lane = mmg_lane();
+	RTree inner;
+	int st = 0, st_inner = 0, i0 = 0, n_alloc = 1, free_head = NIL; /* node 0 is the fake root */
+	inner.nd = nodes, inner.root = NIL;
+	if (max_dist < bw) max_dist = bw;
+	if (max_dist_inner < 0) max_dist_inner = 0;
+	if (max_dist_inner > max_dist) max_dist_inner = max_dist;
+	for (int k = lane; k < n; k += 32) t[k] = 0;
+	__syncwarp();
+#define RN_ALLOC(q) do { if (free_head != NIL) { (q) = free_head; free_head = nodes[free_head].c[0]; } else (q) = n_alloc++; } while (0)
+#define RN_FREE(q) do { nodes[(q)].c[0] = free_head; free_head = (q); } while (0)
+#define RN_PRI(j) (-((double)f[(j)] + __dmul_rn(__dmul_rn(0.5, (double)pen_gap), (double)((int32_t)ax[(j)] + (int32_t)ay[(j)]))))
+	for (int i = 0; i < n; ++i) {
+		const uint64_t aix = ax[i], aiy = ay[i];
+		if (i0 < i && ax[i0] != aix) { /* the anchors [i0, i) come into range */
+			for (int j = i0 + lane; j < i; j += 32) {
+				const unsigned long long b = (unsigned long long)__double_as_longlong(RN_PRI(j));
+				pk[j] = b >> 63 ? ~b : b | 0x8000000000000000ull;
+			}
+			if (lane == 0 && max_dist_inner > 0)
+				for (int j = i0; j < i; ++j) {
+					int r;
+					RN_ALLOC(r);
+					nodes[r].y = (int32_t)ay[j], nodes[r].i = j, nodes[r].pri = RN_PRI(j);
+					rn_insert(&inner, r);
+				}
+			i0 = i;
+			__syncwarp();
+		}
+		while (st < i && ((aix >> 32) != (ax[st] >> 32) || aix > ax[st] + (uint64_t)max_dist || i0 - st > cap_rmq_size)) ++st;
+		if (max_dist_inner > 0) {
+			while (st_inner < i && ((aix >> 32) != (ax[st_inner] >> 32) || aix > ax[st_inner] + (uint64_t)max_dist_inner || i0 - st_inner > cap_rmq_size)) {
+				if (lane == 0) {
+					int q = rn_find(&inner, (int32_t)ay[st_inner], st_inner);
+					if (q != NIL) { q = rn_erase(&inner, q); RN_FREE(q); }
+				}
+				++st_inner;
+			}
+		}
+		/* krmq_rmq(outer, (y - max_dist, INT_MAX), (y, 0)): closed interval in (query position, index) order */
+		const int32_t yi = (int32_t)aiy, ylo = yi - max_dist;
+		unsigned long long best = ~0ull;
+		int bestj = -1, cnt = 0;
+		for (int j = st + lane; j < i0; j += 32) {
+			const int32_t yj = (int32_t)ay[j];
+			if (yj > ylo && (yj < yi || (yj == yi && j == 0))) {
+				const unsigned long long k = pk[j];
+				if (k < best) best = k, bestj = j, cnt = 1;
+				else if (k == best) ++cnt;
+			}
+		}
+		unsigned long long m = best;
+#pragma unroll
+		for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(MMG_FULL, m, d); m = o < m ? o : m; }
+		int qj = -1;
+		if (m != ~0ull) {
+			if (__reduce_add_sync(MMG_FULL, best == m ? cnt : 0) > 1) return 1;   /* the minimum is not unique: the tree decides */
+			const unsigned w = __ballot_sync(MMG_FULL, best == m);
+			qj = __shfl_sync(MMG_FULL, bestj, __ffs((int)w) - 1);
+		}
+		if (lane == 0) {
+			int max_j = -1;
+			int32_t q_span = (int32_t)(aiy >> 32 & 0xff), max_f = q_span;
+			if (qj >= 0) {
+				int32_t sc, exact, width, n_skip = 0;
+				int j = qj;
+				sc = f[j] + rq_sc_simple(aix, aiy, ax[j], ay[j], pen_gap, pen_skip, &exact, &width);
+				if (width <= bw && sc > max_f) max_f = sc, max_j = j;
+				if (!exact && inner.root != NIL && (int32_t)aiy > 0) {
+					/* krmq_interval(root_inner, (y-1, n)): lower = largest node <= key; then iterate downwards */
+					const int32_t ky = (int32_t)aiy - 1, ki = n;
+					int stack[RMQ_MAX_DEPTH], top = -1, lo = NIL, pp = inner.root;
+					while (pp != NIL) {
+						int cmp = rn_cmp(ky, ki, nodes[pp]);
+						if (cmp < 0) pp = nodes[pp].c[0];
+						else if (cmp > 0) lo = pp, pp = nodes[pp].c[1];
+						else { lo = pp; break; }
+					}
+					if (lo != NIL) {
+						pp = inner.root;
+						while (pp != NIL) {
+							stack[++top] = pp;
+							int cmp = rn_cmp(nodes[lo].y, nodes[lo].i, nodes[pp]);
+							if (cmp < 0) pp = nodes[pp].c[0];
+							else if (cmp > 0) pp = nodes[pp].c[1];
+							else break;
+						}
+						while (top >= 0) {
+							int qq = stack[top];
+							if (nodes[qq].y < (int32_t)aiy - max_dist_inner) break;
+							j = nodes[qq].i;
+							sc = f[j] + rq_sc_simple(aix, aiy, ax[j], ay[j], pen_gap, pen_skip, 0, &width);
+							if (width <= bw) {
+								if (sc > max_f) {
+									max_f = sc, max_j = j;
+									if (n_skip > 0) --n_skip;
+								} else if (t[j] == i) {
+									if (++n_skip > max_chn_skip) break;
+								}
+								if (p[j] >= 0) t[p[j]] = i;
+							}
+							{ /* krmq_itr_prev */
+								int c0 = nodes[stack[top]].c[0];
+								if (c0 != NIL) {
+									for (pp = c0; pp != NIL; pp = nodes[pp].c[1]) stack[++top] = pp;
+								} else {
+									int prev;
+									do { prev = stack[top--]; } while (top >= 0 && prev == nodes[stack[top]].c[0]);
+									if (top < 0) break;
+								}
+							}
+						}
+					}
+				}
+			}
+			f[i] = max_f, p[i] = max_j;
+		}
+		__syncwarp();
+	}
+#undef RN_ALLOC
+#undef RN_FREE
+#undef RN_PRI
+	return 0;
+}
+
 __global__ void __launch_bounds__(CHAIN_WARPS * 32)
-rechain_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, uint32_t *work)
+rechain_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, int serial, uint32_t *work)
 {
 	__shared__ int s_bkt[CHAIN_WARPS][512];
 	const int lane = mmg_lane(), wib = threadIdx.x >> 5;
@@ -409,11 +546,18 @@ rechain_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, uin
 		if (!(qlen - (en - st) > o.rmq_rescue_size || (float)(en - st) > __fmul_rn((float)qlen, o.rmq_rescue_ratio))) continue;
 		int n = (int)c.n_v[r], n_v = 0;
 		int32_t *f = c.f + ab, *p = c.p + ab, *t = c.t + ab, *v = c.v + ab;
+		RNode *nd = nodes + 2 * ab + 2 * (uint64_t)r;   /* disjoint per read: 2 nodes per anchor + 2 (the arena holds 2 * (anchors + reads) nodes) */
 		if (lane == 0) {
 			dev_radix_sort_128x(ax, ay, n, s_bkt[wib], (int*)v);
-			dev_lchain_rmq(o.max_gap, o.rmq_inner_dist, o.bw_long, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
-			               n, ax, ay, f, p, t, nodes + 2 * ab + 2 * (uint64_t)r); /* disjoint per read: 2 nodes per anchor + 2 (the arena holds 2 * (anchors + reads) nodes) */
 			c.flags[r] |= 2u;
+		}
+		__syncwarp();
+		/* the warp form needs n + 1 nodes for its one tree; the keys go into the upper half of the read's slice */
+		if (serial || dev_lchain_rmq_warp(o.max_gap, o.rmq_inner_dist, o.bw_long, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
+		                                  n, ax, ay, f, p, t, nd, (unsigned long long*)(nd + n + 2))) {
+			__syncwarp();
+			if (lane == 0)
+				dev_lchain_rmq(o.max_gap, o.rmq_inner_dist, o.bw_long, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip, n, ax, ay, f, p, t, nd);
 		}
 		__syncwarp();
 		dev_backtrack_compact(n, ax, ay, f, p, t, v, c.zx + 2 * ab, c.zy + 2 * ab, c.cx + ab, c.cy + ab, c.u + ab,
@@ -428,7 +572,7 @@ rechain_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, uin
 /* MM_F_RMQ (the asm5 / asm10 / asm20 presets): map.c mm_map_frag chains with mm_lchain_rmq instead of mm_lchain_dp.
  * Same routine as the re-chain step, on the sorted anchors of the read, band bw; backtrack_kernel follows as usual. */
 __global__ void __launch_bounds__(CHAIN_WARPS * 32)
-chain_rmq_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, uint32_t *work)
+chain_rmq_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, int serial, uint32_t *work)
 {
 	const int lane = mmg_lane();
 	for (;;) {
@@ -437,11 +581,24 @@ chain_rmq_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, u
 		r = mmg_read_of(c, r);
 		const int n = (int)c.n_a[r];
 		const uint64_t ab = c.a_off[r] - c.a_off0;
-		if (lane == 0 && n > 0)
-			dev_lchain_rmq(o.max_gap, o.rmq_inner_dist, o.bw, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
-			               n, c.bx + ab, c.by + ab, c.f + ab, c.p + ab, c.t + ab, nodes + 2 * ab + 2 * (uint64_t)r);
+		RNode *nd = nodes + 2 * ab + 2 * (uint64_t)r;
+		if (n > 0 && (serial || dev_lchain_rmq_warp(o.max_gap, o.rmq_inner_dist, o.bw, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
+		                                            n, c.bx + ab, c.by + ab, c.f + ab, c.p + ab, c.t + ab, nd, (unsigned long long*)(nd + n + 2)))) {
+			__syncwarp();
+			if (lane == 0)
+				dev_lchain_rmq(o.max_gap, o.rmq_inner_dist, o.bw, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
+				               n, c.bx + ab, c.by + ab, c.f + ab, c.p + ab, c.t + ab, nd);
+		}
 		__syncwarp();
 	}
+}
+
+/* MMG_RMQ_SERIAL=1: every read through the tree replay (the form the warp version is checked against) */
+static int rmq_serial(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("MMG_RMQ_SERIAL"); v = e && atoi(e) ? 1 : 0; }
+	return v;
 }
 
 int launch_chain_rmq(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, void *nodes, int n_sms, cudaStream_t st, uint32_t *work)
@@ -449,7 +606,7 @@ int launch_chain_rmq(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r
 	int grid = n_sms * 8, need = ((int)(r1 - r0) + CHAIN_WARPS - 1) / CHAIN_WARPS;
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
-	MMG_LAUNCH(chain_rmq_kernel, grid, CHAIN_WARPS * 32, 0, st, c, o, r0, r1, (RNode*)nodes, work);
+	MMG_LAUNCH(chain_rmq_kernel, grid, CHAIN_WARPS * 32, 0, st, c, o, r0, r1, (RNode*)nodes, rmq_serial(), work);
 	return 0;
 }
 
@@ -458,6 +615,6 @@ int launch_rechain(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1,
 	int grid = n_sms * 8, need = ((int)(r1 - r0) + CHAIN_WARPS - 1) / CHAIN_WARPS;
 	if (grid > need) grid = need;
 	if (grid < 1) grid = 1;
-	MMG_LAUNCH(rechain_kernel, grid, CHAIN_WARPS * 32, 0, st, c, o, r0, r1, (RNode*)nodes, work);
+	MMG_LAUNCH(rechain_kernel, grid, CHAIN_WARPS * 32, 0, st, c, o, r0, r1, (RNode*)nodes, rmq_serial(), work);
 	return 0;
 }
