@@ -5,7 +5,7 @@ import collections, csv, json, os, subprocess, sys
 
 STAGE = [("sketch_kernel", "sketch"), ("seed_kernel", "seed"), ("anchor_filter_kernel", "expand"), ("expand_kernel", "expand"),
          ("radix_sort_kernel", "sort"), ("sort_kernel", "sort"), ("chain_dp_kernel", "chain_dp"), ("backtrack_kernel", "backtrack"),
-         ("rechain_kernel", "rechain"), ("regs_kernel", "regs"), ("ext_fill_kernel", "extend"), ("ext_dp_kernel", "extend"), ("ext_prep_kernel", "extend"), ("ext_stitch_kernel", "extend")]
+         ("rechain_kernel", "rechain"), ("regs_kernel", "regs"), ("ext_fill_kernel", "extend"), ("ext_dp_kernel", "extend"), ("ext_prep_kernel", "extend"), ("ext_stitch_kernel", "extend"), ("ext_job_scan_kernel", "extend")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 

@@ -1,6 +1,7 @@
-"""Read sharding for multi-GPU runs: the index is replicated on every GPU, a batch is cut into
-contiguous shards of (nearly) equal BASES (not read counts), every rank maps its shard, results return to the host in
-read order.  There is no collective on the data path."""
+"""Test helper: how a launcher with one process per GPU cuts a batch: contiguous shards of (nearly)
+equal BASES, index replicated, results back in read order, no collective on the data path.  The product does this
+split itself inside `mmg_map_batch` of a multi-device aligner (csrc/pipeline.cu map_batch_group); this copy lets the
+world_size-2 gloo test drive two single-device aligners the way torchrun ranks would."""
 import numpy as np
 
 

@@ -12,7 +12,7 @@ from conftest import EMU_LIB, ROOT
 
 
 def test_split_by_bases_balances_and_covers():
-    from mappy_rs.sharding import split_by_bases
+    from shard_util import split_by_bases
     rs = np.random.RandomState(3)
     lens = rs.randint(100, 10000, 1000)
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
@@ -30,7 +30,7 @@ WORKER = textwrap.dedent('''
     import numpy as np, torch.distributed as dist
     import data_gen, parity
     from mappy_rs import _mmg
-    from mappy_rs.sharding import shard
+    from shard_util import shard
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     lib = _mmg.Lib(r"{emu}")
