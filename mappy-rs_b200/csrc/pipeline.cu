@@ -95,6 +95,8 @@ struct mmg_aligner {
 	DevIndex di;
 	DevOpt dopt;
 	std::vector<void*> dev_allocs;     /* index + arenas */
+	std::vector<uint64_t> dev_alloc_bytes;
+	uint64_t dev_bytes = 0;
 	/* arena capacities */
 	uint64_t cap_bases, cap_anchors, cap_regs, cap_keep_words;
 	int dual_min;                      /* fewest reads of a chunk for which the two-stream split is used */
@@ -104,7 +106,7 @@ struct mmg_aligner {
 	int ramp_shift;                    /* streamed mode: the first chunk is 1/2^ramp_shift of the arena (tuning knob "ramp_shift") */
 	int anchor_filter;                 /* 1 = drop isolated anchors before the sort (seed.cu anchor_filter_kernel) */
 	uint32_t cap_reads;
-	bool arenas_ready;
+	bool arenas_ready, caps_auto;
 	ChunkDev cd;                       /* arena pointers */
 	unsigned char *rmq_nodes;          /* AVL node arena of the re-chain stage */
 	uint32_t *d_order;                 /* longest-first work order of the chunk's reads */
@@ -166,9 +168,12 @@ template<typename T> static int dev_alloc(mmg_aligner *al, T **p, uint64_t n)
 {
 	void *q = 0;
 	if (n == 0) n = 1;
+	if (const char *lim = getenv("MMG_ALLOC_LIMIT")) { /* test hook: a device with this many bytes left for this aligner */
+		if (al->dev_bytes + n * sizeof(T) > strtoull(lim, 0, 10)) { mmg_set_error("cudaMalloc of %llu bytes refused (MMG_ALLOC_LIMIT)", (unsigned long long)(n * sizeof(T))); return MMG_ENOMEM; }
+	}
 	cudaError_t e = cudaMalloc(&q, n * sizeof(T));
 	if (e != cudaSuccess) { mmg_set_error("cudaMalloc of %llu bytes failed: %s", (unsigned long long)(n * sizeof(T)), cudaGetErrorString(e)); return MMG_ENOMEM; }
-	al->dev_allocs.push_back(q);
+	al->dev_allocs.push_back(q), al->dev_alloc_bytes.push_back(n * sizeof(T)), al->dev_bytes += n * sizeof(T);
 	*p = (T*)q;
 	if (getenv("MMG_POISON")) cudaMemset(q, 0xCD, n * sizeof(T)), cudaDeviceSynchronize(); /* test hook: nothing may depend on what cudaMalloc returns */
 	return MMG_OK;
@@ -253,9 +258,8 @@ static void fill_devopt(mmg_aligner *al)
 	o.max_sw_mat = m.max_sw_mat;
 }
 
-static int alloc_arenas(mmg_aligner *al)
+static int alloc_arenas_once(mmg_aligner *al)
 {
-	if (al->arenas_ready) return MMG_OK;
 	ChunkDev &c = al->cd;
 	const uint64_t B = al->cap_bases, A = al->cap_anchors, R = al->cap_reads, G = al->cap_regs;
 	int rc = 0;
@@ -285,6 +289,31 @@ static int alloc_arenas(mmg_aligner *al)
 #undef AL
 	al->arenas_ready = true;
 	return MMG_OK;
+}
+
+/* The default arena sizes assume the aligner has the device to itself (a B200: 121 GB with CIGAR).  When the memory is
+ * not there - another aligner on the same GPU, a smaller device - the allocation is rolled back and repeated one size
+ * down: chunks of 192, 96, 48 Mbases, then with a smaller traceback arena.  Sizes set through mmg_aligner_set are the
+ * caller's: they are tried once. */
+static int alloc_arenas(mmg_aligner *al)
+{
+	if (al->arenas_ready) return MMG_OK;
+	for (;;) {
+		const size_t mark = al->dev_allocs.size();
+		const int rc = alloc_arenas_once(al);
+		if (rc == MMG_OK) return MMG_OK;
+		while (al->dev_allocs.size() > mark) { cudaFree(al->dev_allocs.back()); al->dev_bytes -= al->dev_alloc_bytes.back(); al->dev_allocs.pop_back(), al->dev_alloc_bytes.pop_back(); }
+		cudaGetLastError();
+		if (rc != MMG_ENOMEM || !al->caps_auto) return rc;
+		if (al->cap_bases > ((uint64_t)48 << 20)) {
+			al->cap_bases >>= 1, al->cap_anchors >>= 1;
+			if (al->cap_reads > (1u << 17)) al->cap_reads >>= 1;
+			if (al->cap_regs > ((uint64_t)4 << 20)) al->cap_regs >>= 1;
+			if (al->cap_keep_words > ((uint64_t)1 << 22)) al->cap_keep_words >>= 1;
+			al->cap_cg = (uint64_t)3 * al->cap_bases, al->cap_jobs = al->cap_bases / 48;
+		} else if (al->cap_tb > ((uint64_t)4 << 30)) al->cap_tb >>= 1;
+		else return rc;
+	}
 }
 
 /* counting sort of the chunk's reads by length / 64, longest first (one CTA; ties in any order) */
@@ -373,7 +402,7 @@ static int aligner_create_on(const mmg_index *idx, const mmg_mapopt_t *mo, int d
 	al->ev_used = 0, al->s_in = 0, al->s_out = 0, al->stream_ready = false, al->d_stats_pool = 0, al->n_sub = 0;
 	memset(al->in_bases, 0, sizeof(al->in_bases)), memset(al->in_off, 0, sizeof(al->in_off)), memset(al->h_in_off, 0, sizeof(al->h_in_off));
 	memset(al->ev_in, 0, sizeof(al->ev_in)), memset(al->ev_free, 0, sizeof(al->ev_free)), memset(al->rs, 0, sizeof(al->rs));
-	al->arenas_ready = false;
+	al->arenas_ready = false, al->caps_auto = true;
 	al->profile = 0;
 	al->cap_bases = (uint64_t)96 << 20, al->cap_reads = 1u << 17, al->cap_anchors = (uint64_t)48 << 20, al->cap_regs = (uint64_t)4 << 20;
 	al->cap_keep_words = (uint64_t)1 << 22; /* unfiltered anchors per chunk the isolated-anchor filter can look at: 2^27, 2^29 on a 180 GB device */
@@ -512,6 +541,7 @@ int mmg_aligner_set(mmg_aligner *al, const char *key, int64_t v)
 	if (strcmp(key, "dual_min") == 0) { al->dual_min = v < 2 ? 2 : (int)v; return MMG_OK; }
 	if (strcmp(key, "ramp_shift") == 0) { al->ramp_shift = v < 0 ? 0 : v > 6 ? 6 : (int)v; return MMG_OK; }
 	if (al->arenas_ready) { mmg_set_error("arena sizes are fixed after the first batch"); return MMG_EINVAL; }
+	al->caps_auto = false;   /* the caller sizes the arenas: no stepping down on its behalf */
 	if (strcmp(key, "chunk_bases") == 0) al->cap_bases = (uint64_t)v;
 	else if (strcmp(key, "chunk_reads") == 0) al->cap_reads = (uint32_t)v;
 	else if (strcmp(key, "anchor_cap") == 0) al->cap_anchors = (uint64_t)v;
@@ -668,7 +698,7 @@ static int stream_setup(mmg_aligner *al)
 		CK(cudaEventCreateWithFlags(&al->rs[k].ev_out, cudaEventDisableTiming));
 	}
 	if (cudaMalloc((void**)&al->d_stats_pool, MMG_N_STATS * 8) != cudaSuccess) { mmg_set_error("cudaMalloc failed"); return MMG_ENOMEM; }
-	al->dev_allocs.push_back(al->d_stats_pool);
+	al->dev_allocs.push_back(al->d_stats_pool), al->dev_alloc_bytes.push_back(0);
 	al->stream_ready = true;
 	return MMG_OK;
 }

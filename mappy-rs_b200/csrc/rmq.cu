@@ -400,7 +400,7 @@ __device__ void dev_lchain_rmq(int max_dist, int max_dist_inner, int bw, int max
  * in key order with the n_skip / t[] logic) is kept as it is, on lane 0.  Priorities are compared as order-preserving
  * 64-bit keys of the very doubles upstream computes. */
 __device__ int dev_lchain_rmq_warp(int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, float pen_gap, float pen_skip,
-                                   int n, const uint64_t *ax, const uint64_t *ay, int32_t *f, int32_t *p, int32_t *t, RNode *nodes, unsigned long long *pk)
+                                   int n, const uint64_t *ax, const uint64_t *ay, int32_t *f, int32_t *p, int32_t *t, RNode *nodes, unsigned long long *pk, int fake_tie_at)
 {
 	const int lane = mmg_lane();
 	RTree inner;
@@ -457,6 +457,7 @@ __device__ int dev_lchain_rmq_warp(int max_dist, int max_dist_inner, int bw, int
 #pragma unroll
 		for (int d = 16; d; d >>= 1) { const unsigned long long o = __shfl_xor_sync(MMG_FULL, m, d); m = o < m ? o : m; }
 		int qj = -1;
+		if (fake_tie_at > 0 && i + 1 == fake_tie_at) return 1;
 		if (m != ~0ull) {
 			if (__reduce_add_sync(MMG_FULL, best == m ? cnt : 0) > 1) return 1;   /* the minimum is not unique: the tree decides */
 			const unsigned w = __ballot_sync(MMG_FULL, best == m);
@@ -553,8 +554,8 @@ rechain_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, int
 		}
 		__syncwarp();
 		/* the warp form needs n + 1 nodes for its one tree; the keys go into the upper half of the read's slice */
-		if (serial || dev_lchain_rmq_warp(o.max_gap, o.rmq_inner_dist, o.bw_long, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
-		                                  n, ax, ay, f, p, t, nd, (unsigned long long*)(nd + n + 2))) {
+		if ((serial & 1) || dev_lchain_rmq_warp(o.max_gap, o.rmq_inner_dist, o.bw_long, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
+		                                        n, ax, ay, f, p, t, nd, (unsigned long long*)(nd + n + 2), serial >> 1)) {
 			__syncwarp();
 			if (lane == 0)
 				dev_lchain_rmq(o.max_gap, o.rmq_inner_dist, o.bw_long, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip, n, ax, ay, f, p, t, nd);
@@ -582,8 +583,8 @@ chain_rmq_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, i
 		const int n = (int)c.n_a[r];
 		const uint64_t ab = c.a_off[r] - c.a_off0;
 		RNode *nd = nodes + 2 * ab + 2 * (uint64_t)r;
-		if (n > 0 && (serial || dev_lchain_rmq_warp(o.max_gap, o.rmq_inner_dist, o.bw, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
-		                                            n, c.bx + ab, c.by + ab, c.f + ab, c.p + ab, c.t + ab, nd, (unsigned long long*)(nd + n + 2)))) {
+		if (n > 0 && ((serial & 1) || dev_lchain_rmq_warp(o.max_gap, o.rmq_inner_dist, o.bw, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
+		                                                  n, c.bx + ab, c.by + ab, c.f + ab, c.p + ab, c.t + ab, nd, (unsigned long long*)(nd + n + 2), serial >> 1))) {
 			__syncwarp();
 			if (lane == 0)
 				dev_lchain_rmq(o.max_gap, o.rmq_inner_dist, o.bw, o.max_chain_skip, o.rmq_size_cap, o.chn_pen_gap, o.chn_pen_skip,
@@ -593,12 +594,13 @@ chain_rmq_kernel(ChunkDev c, DevOpt o, uint32_t r0, uint32_t r1, RNode *nodes, i
 	}
 }
 
-/* MMG_RMQ_SERIAL=1: every read through the tree replay (the form the warp version is checked against) */
+/* MMG_RMQ_SERIAL=1: every read through the tree replay (the form the warp version is checked against);
+ * MMG_RMQ_SERIAL=2k (k > 0): the warp version pretends a tie at its k-th anchor, so that tests walk the
+ * "abandon the read half way and replay it" path, which real ties take too rarely to rely on.  Read per launch. */
 static int rmq_serial(void)
 {
-	static int v = -1;
-	if (v < 0) { const char *e = getenv("MMG_RMQ_SERIAL"); v = e && atoi(e) ? 1 : 0; }
-	return v;
+	const char *e = getenv("MMG_RMQ_SERIAL");
+	return e ? atoi(e) : 0;
 }
 
 int launch_chain_rmq(const ChunkDev &c, const DevOpt &o, uint32_t r0, uint32_t r1, void *nodes, int n_sms, cudaStream_t st, uint32_t *work)

@@ -119,6 +119,50 @@ def test_repeats_chimeras_and_rechain(emu_lib, oracle_mod):
         c.close()
 
 
+@pytest.mark.parametrize("mode", ["1", "14", "200"])
+def test_rechain_tree_replay_paths(emu_lib, oracle_mod, mode, monkeypatch):
+    """mm_lchain_rmq on the device answers the outer range-minimum with a warp scan and falls back to the replay of
+    krmq's AVL tree when the minimum is tied.  MMG_RMQ_SERIAL=1 sends every read through the tree; 2k makes the warp
+    form give up at its k-th anchor (early / deep inside a read), so the abandon-and-replay path is walked on purpose.
+    All three must give what the default gives: the oracle's chains."""
+    monkeypatch.setenv("MMG_RMQ_SERIAL", mode)
+    ref, coff, names, seqs = parity.random_reference(41, [300000, 150000], n_repeats=60, rep_min=300, rep_max=4000, rep_div=0.03)
+    c = parity.Case(emu_lib, names, seqs)
+    try:
+        buf, offs = data_gen.make_sv_reads(51, ref, coff, 120)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert ora.stats["n_rechain"] > 40
+        assert parity.compare_stats(dev, ora) == []
+        assert parity.compare_hits(dev, ora) == []
+    finally:
+        c.close()
+
+
+def test_arenas_step_down_when_the_device_is_short_of_memory(emu_lib, oracle_mod, monkeypatch):
+    """The default arenas assume the aligner owns the GPU.  With less memory left (another aligner on the device; here
+    MMG_ALLOC_LIMIT plays that part) the allocation is rolled back and repeated one size down until it fits - smaller
+    chunks, then a smaller traceback arena - and the results are the same; sizes the caller set are not second-guessed."""
+    ref, coff, names, seqs = parity.random_reference(17, [200000])
+    buf, offs, _ = data_gen.make_reads(18, ref, coff, 40, 500, 5000)
+    c = parity.Case(emu_lib, names, seqs, cigar=True)
+    try:
+        ora = c.oracle.map_batch(buf, offs, 4)
+        monkeypatch.setenv("MMG_ALLOC_LIMIT", str(14 << 30))      # the stock sizes of the test device need ~60 GB
+        dev = c.aligner.map_batch(buf, offs)
+        assert parity.compare_hits(dev, ora) == []
+    finally:
+        c.close()
+    c = parity.Case(emu_lib, names, seqs, cigar=True)
+    try:
+        c.aligner.set("tb_cap", 1 << 34)
+        monkeypatch.setenv("MMG_ALLOC_LIMIT", str(1 << 30))
+        with pytest.raises(RuntimeError, match="MMG_ALLOC_LIMIT"):
+            c.aligner.map_batch(buf, offs)
+    finally:
+        c.close()
+
+
 def _small_arenas(c):
     for k, v in (("tb_cap", 1 << 28), ("cigar_cap", 1 << 24), ("jobs_cap", 1 << 16), ("chunk_bases", 1 << 22),
                  ("anchor_cap", 1 << 20), ("chunk_reads", 4096), ("regs_cap", 1 << 16), ("big_per_warp", 1 << 18)):
