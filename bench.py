@@ -271,11 +271,12 @@ def measure_mode(args, lib, idx, mopt_base, cigar, views, n_reads, n_bases, loca
     peak, how = measured_peak()
     algo = ALGO_BYTES[top](stats)
     achieved = algo / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
-    n_launch = max(1, stage_ln.get(top, 1) // args.steps)
+    # one "launch" of a stage = its kernels over one chunk (what profiles/traffic.json sums, too); every chunk runs the sketch stage once
+    n_launch = max(1, stage_ln.get("sketch", stage_ln.get(top, 1)) // args.steps)
     tr = load_traffic().get(("cigar:" if cigar else "") + top) or load_traffic().get(top)
     out["roofline"] = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                        "traffic": tr["dram_bytes_per_launch"] if tr else None, "peak_source": "of " + how, "ms_per_step": top_ms, "launches_per_step": n_launch,
-                       "algorithmic_bytes_per_launch": algo / n_launch, "ms_per_launch": top_ms / n_launch, "traffic_source": (tr or {}).get("report"),
+                       "algorithmic_bytes_per_launch": algo / n_launch, "ms_per_launch": top_ms / n_launch, "traffic_source": (tr or {}).get("report"), "traffic_excludes": (tr or {}).get("kernels_without_dram_counters") or None,
                        "note": "achieved = algorithmic bytes of the stage per step (BASELINE.md; anchors after the isolated-anchor filter) / its summed event time. "
                                "This stage is integer-issue bound: see int32_roofline"}
     out["int32_roofline"] = {}

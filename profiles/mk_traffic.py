@@ -20,6 +20,7 @@ def main():
     h, units = rows[0], rows[1]
     kn, rd, wr, du = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
     per = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    missing = collections.defaultdict(list)
     n_chunks = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # stage launches (chunks) the capture covers
     seen_sketch = 0
     for r in rows[2:]:
@@ -32,10 +33,13 @@ def main():
             continue
         b = float(r[rd].replace(",", "")) * UNIT.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * UNIT.get(units[wr], 1.0)
         per[st][0] += 1
+        if b != b:   # ncu returned no dram counters for this launch (seen on ext_fill_kernel<6>): say so instead of summing a NaN
+            missing[st].append(r[kn].split("(")[0])
+            b = 0.0
         per[st][1] += b
         per[st][2] += float(r[du].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[du], 1.0)
     out = {st: {"dram_bytes_per_launch": v[1] / n_chunks, "kernels_captured": v[0], "stage_launches_captured": n_chunks, "ms_under_ncu_per_launch": v[2] / n_chunks,
-                "report": os.path.basename(rep), "workload": tag} for st, v in per.items()}
+                "report": os.path.basename(rep), "workload": tag, "kernels_without_dram_counters": missing.get(st, [])} for st, v in per.items()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print(json.dumps(out, indent=1, sort_keys=True))
