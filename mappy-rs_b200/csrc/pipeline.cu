@@ -300,7 +300,17 @@ static int alloc_arenas(mmg_aligner *al)
 	if (al->arenas_ready) return MMG_OK;
 	for (;;) {
 		const size_t mark = al->dev_allocs.size();
-		const int rc = alloc_arenas_once(al);
+		int rc = alloc_arenas_once(al);
+#ifndef MMG_EMU
+		if (rc == MMG_OK && al->caps_auto) { /* what is still to come: two input slots of a chunk each, the result slots, per-batch buffers */
+			size_t free_b = 0, total_b = 0;
+			const uint64_t reserve = 2 * al->cap_bases + ((uint64_t)6 << 30);
+			if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b < reserve) {
+				mmg_set_error("only %llu MB of device memory would be left after the arenas", (unsigned long long)(free_b >> 20));
+				al->arenas_ready = false, rc = MMG_ENOMEM;
+			}
+		}
+#endif
 		if (rc == MMG_OK) return MMG_OK;
 		while (al->dev_allocs.size() > mark) { cudaFree(al->dev_allocs.back()); al->dev_bytes -= al->dev_alloc_bytes.back(); al->dev_allocs.pop_back(), al->dev_alloc_bytes.pop_back(); }
 		cudaGetLastError();
