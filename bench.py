@@ -314,14 +314,18 @@ def run_group(args, lib, io, mopt, idx, ref, coff, names, preset, hbuf, offs, ra
         setup_s = time.perf_counter() - t0
         bufs, lens = [hbuf.numpy()], [np.diff(offs.astype(np.int64))]
         big = args.workload in ("human", "human-repeats") or args.ref == "human"
-        for r in range(1, world):   # the reads the other ranks mapped (same seeds)
+        def reads_of(r):   # the reads rank r mapped (same seeds); the simulator is C code that releases the GIL
             if args.workload == "hifi":
                 b, o, _ = data_gen.make_reads(5 + 1000 * r, ref, coff, args.reads, 10000, 25000, len_mean=15000.0, len_sd=2000.0, p_sub=0.002, p_ins=0.0015, p_del=0.0015)
             else:
                 b, o, _ = data_gen.make_reads((4 if big else 2) + 1000 * r, ref, coff, args.reads, 1000, 10000, p_sub=0.03, p_ins=0.02, p_del=0.03)
                 if args.workload == "prefix":
                     b, o = data_gen.prefixes(b, o, 400)
-            bufs.append(b), lens.append(np.diff(o.astype(np.int64)))
+            return b, np.diff(o.astype(np.int64))
+        import concurrent.futures
+        with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(world - 1, 8))) as ex:
+            for b, l in ex.map(reads_of, range(1, world)):
+                bufs.append(b), lens.append(l)
         n_all = int(sum(len(x) for x in lens))
         goffs = np.zeros(n_all + 1, dtype=np.uint64)
         goffs[1:] = np.cumsum(np.concatenate(lens))
