@@ -124,6 +124,50 @@ def _mappings_of_batch(res, names, lens, cs_list, md_list, n_reads):
     return [out_hits[ho[i]:ho[i + 1]] for i in range(n_reads)]
 
 
+class BatchMappings:
+    """What `Aligner.map_arrays` returns: the hits of one device batch, kept as the library returned them - `hits`
+    (structured array of mmg_hit_t), `cigar` (packed uint32, len << 4 | op), `hit_off` (hits of read i are
+    hit_off[i] .. hit_off[i + 1]) are views of the page-locked result block, nothing is copied or converted.  Indexing
+    or iterating materialises `Mapping` objects for the reads asked for only."""
+
+    def __init__(self, res, names, lens, cs_list, md_list, n_reads):
+        self._res, self._names, self._lens, self._cs, self._md, self._n = res, names, lens, cs_list, md_list, n_reads
+        self.hits, self.cigar, self.hit_off = res.hits, res.cigar, res.hit_off
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        out = []
+        for k in range(int(self.hit_off[i]), int(self.hit_off[i + 1])):
+            h = self.hits[k]
+            c0, rid = int(h["cigar_off"]), int(h["rid"])
+            out.append(Mapping(int(h["qs"]), int(h["qe"]), -1 if h["rev"] else 1, self._names[rid], self._lens[rid], int(h["rs"]), int(h["re"]),
+                               int(h["mlen"]), int(h["blen"]), int(h["mapq"]), bool(h["is_primary"]), self.cigar[c0:c0 + int(h["n_cigar"])],
+                               int(h["nm"]), self._md[k] if self._md is not None else None, self._cs[k] if self._cs is not None else None))
+        return out
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+    def cs(self, k):
+        """cs string of hit k (bytes as generated; None if not requested)"""
+        return None if self._cs is None else self._cs[k]
+
+    def close(self):
+        """returns the result block to the aligner's pool (also done when the object is collected)"""
+        self.hits = self.cigar = self.hit_off = None
+        if self._res is not None:
+            self._res.close()
+            self._res = None
+
+
 class AlignmentBatchResultIter:
     """Iterator returned by map_batch (lib.rs:923-992): yields (list[Mapping], dict) in completion order."""
 
@@ -273,6 +317,34 @@ class Aligner:
             cs_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 0) if cs else None   # reads the shared pinned buffer
             md_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 1) if md else None
         return _mappings_of_batch(res, self._names, self._lens, cs_l, md_l, n)
+
+    def pinned_buffer(self, n_bytes):
+        """A page-locked numpy uint8 array of n_bytes the caller can assemble a batch in (a FASTQ reader writing its
+        records back to back): `map_arrays` on it copies nothing on the host.  Valid until the next call."""
+        return self._pinned.view(int(n_bytes))[:int(n_bytes)]
+
+    def map_arrays(self, bases, offsets, cs=True, MD=False):
+        """Bulk entry next to the reference's API: `bases` holds the reads back to back
+        (bytes, bytearray, memoryview or numpy uint8; ASCII), `offsets` has n + 1 entries.  Returns a `BatchMappings`:
+        raw result arrays plus `Mapping` objects on demand.  No per-read dict, str or Mapping is created here."""
+        if self._index is None:
+            raise RuntimeError("No index")
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if offs.ndim != 1 or len(offs) < 1 or (len(offs) > 1 and (np.diff(offs.astype(np.int64)) <= 0).any()):
+            raise ValueError("`offsets` must be increasing, one more than the number of reads (an empty read: 'Sequence is empty')")
+        src = bases if isinstance(bases, np.ndarray) else np.frombuffer(bases, dtype=np.uint8)
+        if src.dtype != np.uint8 or src.ndim != 1 or int(offs[-1]) > len(src):
+            raise ValueError("`bases` must be a flat uint8 / bytes buffer that covers offsets[-1]")
+        n = len(offs) - 1
+        with self._lock:
+            mine = self._pinned.arr is not None and src.ctypes.data == self._pinned.arr.ctypes.data
+            buf = src if mine else self._pinned.view(int(offs[-1]))
+            if not mine and offs[-1]:
+                buf[:int(offs[-1])] = src[:int(offs[-1])]
+            res = self._aligner.map_batch(buf, offs, zero_copy=True)
+            cs_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 0) if cs else None
+            md_l = _mmg.gen_tags(self._lib, self._index, buf, offs, res, 1) if MD else None
+        return BatchMappings(res, self._names, self._lens, cs_l, md_l, n)
 
     def map(self, seq, seq2=None, cs=False, MD=False):
         """Map a single read, blocking (lib.rs:472-514)."""

@@ -212,3 +212,31 @@ def test_results_stream_while_the_producer_is_still_feeding(aligner):
     out = list(box["it"])
     assert len(out) == len(recs) and early >= 4, (len(out), early)
     assert sorted(d["id"] for _, d in out) == list(range(len(recs)))
+
+
+def test_map_arrays_is_the_same_answer_without_per_read_objects(aligner):
+    """a bulk entry next to the reference's API.  Reads back to back in one buffer (here
+    assembled in the aligner's page-locked buffer: no host copy), results as raw arrays with `Mapping`s on demand; every
+    field, CIGAR and cs must equal what `map()` returns read by read."""
+    import numpy as np
+    aligner, _ = aligner
+    reads = [r["seq"] for r in contig_records(2)] + [BACILLUS[:300], ENTEROCOCCUS[50:350]]
+    lens = [len(s) for s in reads]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    buf = aligner.pinned_buffer(int(offs[-1]))
+    buf[:] = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+    res = aligner.map_arrays(buf, offs, cs=True, MD=True)
+    assert len(res) == len(reads) and len(res.hits) == int(res.hit_off[-1])
+    for i, s in enumerate(reads):
+        assert res[i] == aligner.map(s, cs=True, MD=True), i
+    assert [len(m) for m in res] == [len(res[i]) for i in range(len(res))]
+    res.close()
+    # from plain bytes (copied once into the page-locked buffer), without tags
+    res2 = aligner.map_arrays("".join(reads).encode(), offs, cs=False)
+    assert [[(m.target_name, m.target_start, m.target_end, m.NM) for m in ms] for ms in res2] == \
+           [[(m.target_name, m.target_start, m.target_end, m.NM) for m in aligner.map(s)] for s in reads]
+    assert all(m.cs is None for ms in res2 for m in ms)
+    with pytest.raises(ValueError):
+        aligner.map_arrays(buf, np.array([0, 10, 10], dtype=np.uint64))     # an empty read
+    with pytest.raises(ValueError):
+        aligner.map_arrays(b"ACGT", np.array([0, 400], dtype=np.uint64))    # offsets beyond the buffer
