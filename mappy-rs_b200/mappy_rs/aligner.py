@@ -149,7 +149,8 @@ class BatchMappings:
             h = self.hits[k]
             c0, rid = int(h["cigar_off"]), int(h["rid"])
             out.append(Mapping(int(h["qs"]), int(h["qe"]), -1 if h["rev"] else 1, self._names[rid], self._lens[rid], int(h["rs"]), int(h["re"]),
-                               int(h["mlen"]), int(h["blen"]), int(h["mapq"]), bool(h["is_primary"]), self.cigar[c0:c0 + int(h["n_cigar"])],
+                               int(h["mlen"]), int(h["blen"]), int(h["mapq"]), bool(h["is_primary"]),
+                               self.cigar[c0:c0 + int(h["n_cigar"])].copy(),   # a Mapping may outlive the result block
                                int(h["nm"]), self._md[k] if self._md is not None else None, self._cs[k] if self._cs is not None else None))
         return out
 
