@@ -252,6 +252,34 @@ def test_cigar_mode_ambiguous_bases_and_long_gaps(emu_lib, oracle_mod):
         c.close()
 
 
+@pytest.mark.parametrize("ov", [dict(sc_ambi=0), dict(sc_ambi=3, a=3, b=5), dict(q=0, e=3, q2=10, e2=1), dict(a=1, b=9, q=16, e=2, q2=41, e2=1)],
+                         ids=["sc_ambi0", "sc_ambi3", "free_gap_open", "asm_like"])
+def test_fill_score_from_cigar_under_odd_scorings(emu_lib, oracle_mod, ov):
+    """The gap-fill kernel re-derives H(tlen-1, qlen-1) from the walked CIGAR: matches, mismatches and N pairs as the DP
+    scored them (an N pair counts -e2 inside ksw_extd2 when sc_ambi is 0, not 0), each gap at the cheaper of the two
+    affine costs.  That has to hold for every scoring a caller can pass (src/lib.rs:360-385): zero gap-open (adjacent
+    gaps of the two kinds tie), sc_ambi 0 and large, a long_thres far from map-ont's.  dp_score, dp_max and mapq of every
+    hit depend on it."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    ref, coff, names, seqs = parity.random_reference(64, [120000])
+    refb = bytearray(seqs[0].encode() if isinstance(seqs[0], str) else seqs[0])
+    for p0 in rng.integers(1000, len(refb) - 1000, 60):
+        refb[p0:p0 + 4] = b"NNNN"
+    seqs = [bytes(refb).decode()]
+    c = parity.Case(emu_lib, names, seqs, cigar=True, overrides=ov)
+    try:
+        _small_arenas(c)
+        buf, offs, _ = data_gen.make_reads(79, ref, coff, 40, 800, 3000)
+        buf = data_gen.sprinkle_n(buf, 9, 0.002)
+        dev = c.aligner.map_batch(buf, offs)
+        ora = c.oracle.map_batch(buf, offs, 4)
+        assert parity.compare_hits(dev, ora) == []
+        assert dev.stats["n_cell_fill"] > 0 and len(ora.hits) >= 30
+    finally:
+        c.close()
+
+
 def test_cigar_mode_fixture_map_one(emu_lib, oracle_mod):
     """`map_one` through the product's kernel source: 1 hit, 0..400, 400M (src/lib.rs:1094-1106)."""
     c = parity.Case(emu_lib, None, None, mmi=MMI, cigar=True)
